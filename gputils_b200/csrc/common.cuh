@@ -1,0 +1,84 @@
+// Shared plumbing for libgputils_b200: context layout, error macros, small device helpers.
+// Internal header -- the public boundary is include/gputils_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include <deque>
+#include <vector>
+
+#include "gputils_b200.h"
+
+#define GPUB_SCRATCH_BYTES (64u * 1024u)
+#define GPUB_HOSTBUF_BYTES 256u
+
+struct gpub_stream_slot {
+    cudaStream_t stream = nullptr;
+    bool owned = false;
+    void *d_scratch = nullptr;         // GPUB_SCRATCH_BYTES of device scratch (reduction partials)
+    unsigned int *d_counter = nullptr; // "last block" ticket, always left at zero
+    void *h_result = nullptr;          // pinned + mapped host buffer the final block writes into
+};
+
+struct gpub_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    std::deque<gpub_stream_slot> slots;  // deque: growing never moves existing slots
+    std::mutex mu;
+};
+
+#define GPUB_CUDA(expr)                              \
+    do {                                             \
+        cudaError_t gpub_e_ = (expr);                \
+        if (gpub_e_ != cudaSuccess) return (int) gpub_e_; \
+    } while (0)
+
+#define GPUB_LAUNCH_CHECK() GPUB_CUDA(cudaGetLastError())
+
+// Makes ctx->device current for the lifetime of the guard (one-process-per-GPU callers never switch).
+struct gpub_device_guard {
+    int prev = -1;
+    bool switched = false;
+    explicit gpub_device_guard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            switched = (cudaSetDevice(dev) == cudaSuccess);
+        }
+    }
+    ~gpub_device_guard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+// Resolves (ctx, sidx) to a usable slot, creating streams lazily. Returns nullptr on bad arguments.
+gpub_stream_slot *gpub_slot(gpub_ctx_t ctx, int sidx, int *err);
+
+#define GPUB_ENTER(ctx, sidx)                              \
+    if (!(ctx)) return GPUB_EINVAL;                        \
+    gpub_device_guard gpub_guard_((ctx)->device);          \
+    int gpub_slot_err_ = 0;                                \
+    gpub_stream_slot *slot = gpub_slot((ctx), (sidx), &gpub_slot_err_); \
+    if (!slot) return gpub_slot_err_;                      \
+    cudaStream_t stream = slot->stream;                    \
+    (void) stream
+
+template<typename T>
+__device__ __forceinline__ T gpub_abs(T x) { return x < T(0) ? -x : x; }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// 64-bit mix (splitmix64 finaliser): the counter-based generator of gpub_fill_uniform_*.
+__host__ __device__ __forceinline__ uint64_t gpub_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// uniform in [0,1) with 53 bits, identical on host and device (the oracle mirrors it in numpy)
+__host__ __device__ __forceinline__ double gpub_u01(uint64_t seed, uint64_t i) {
+    uint64_t h = gpub_mix64(seed ^ gpub_mix64(i));
+    return (double) (h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+static inline size_t gpub_ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,421 @@
+// Batched GEMM  C_i <- beta*C_i + alpha*A_i*B_i  (column-major, NN).
+// Replaces cublas{D,S}gemmBatched / cublas{D,S}gemm (ref: tensor.cuh:1286-1338).
+//
+// Three kernel families, picked by shape in launch():
+//   k_gemm_small  : m, n, k <= 32 and densely packed batches -- HBM-bound (AI = 2n/(3s) flop/B).
+//                   A CTA streams a chunk of whole matrices through shared memory with 128-bit loads,
+//                   each thread owns RT rows x 1 column of one C_i in registers.
+//   k_gemm_dmma   : fp64, tile 64x64 per CTA, FP64 tensor-core tiles (mma.sync m8n8k4 -> DMMA.8x8x4),
+//                   cp.async double-buffered K panels. Used once the problem is a dense contraction.
+//   k_gemm_tiled  : everything else (any m, n, k, ld, stride), 64x64 tile, 4x4 per thread, FFMA/DFMA.
+// FP32 never uses TF32: products and sums are plain FFMA so results track cuBLAS' SGEMM.
+// C may alias B (Nullspace::project, tensor.cuh:2084): the small kernel reads every operand of a
+// chunk before writing; the tiled kernels go through a stream-ordered scratch copy of B in that case.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// small matrices: chunk of whole matrices per CTA
+// ------------------------------------------------------------------------------------------
+template<typename T> struct Vec16;
+template<> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template<> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+
+// cooperative copy of `count` contiguous elements global -> shared (128-bit when both are aligned)
+template<typename T>
+__device__ __forceinline__ void stage_in(T *dst, const T *__restrict__ src, size_t count, int tid, int nthreads) {
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::N;
+    if (((((uintptr_t) src) | ((uintptr_t) dst)) & 15u) == 0) {
+        size_t nv = count / VN;
+        const V *s = reinterpret_cast<const V *>(src);
+        V *d = reinterpret_cast<V *>(dst);
+        for (size_t i = tid; i < nv; i += nthreads) d[i] = s[i];
+        for (size_t i = nv * VN + tid; i < count; i += nthreads) dst[i] = src[i];
+    } else {
+        for (size_t i = tid; i < count; i += nthreads) dst[i] = src[i];
+    }
+}
+
+template<typename T>
+__device__ __forceinline__ void stage_out(T *__restrict__ dst, const T *src, size_t count, int tid, int nthreads) {
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::N;
+    if (((((uintptr_t) src) | ((uintptr_t) dst)) & 15u) == 0) {
+        size_t nv = count / VN;
+        const V *s = reinterpret_cast<const V *>(src);
+        V *d = reinterpret_cast<V *>(dst);
+        for (size_t i = tid; i < nv; i += nthreads) d[i] = s[i];
+        for (size_t i = nv * VN + tid; i < count; i += nthreads) dst[i] = src[i];
+    } else {
+        for (size_t i = tid; i < count; i += nthreads) dst[i] = src[i];
+    }
+}
+
+// RT = rows of C kept in registers per thread (>= m, power of two); one thread = one column of one C_i.
+// Shared layout per chunk: A (mpc * m*k), B (mpc * k*n), C (mpc * m*n) exactly as in global memory.
+template<typename T, int RT>
+__global__ void __launch_bounds__(256) k_gemm_small(int m, int n, int k, T alpha, const T *__restrict__ A,
+                                                     const T *__restrict__ B, T beta, T *C, size_t batch, int mpc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sA = reinterpret_cast<T *>(smem_raw);
+    const size_t szA = (size_t) m * k, szB = (size_t) k * n, szC = (size_t) m * n;
+    // keep each region 16-byte aligned
+    const size_t offB = (szA * mpc * sizeof(T) + 15) / 16 * 16 / sizeof(T);
+    const size_t offC = offB + (szB * mpc * sizeof(T) + 15) / 16 * 16 / sizeof(T);
+    T *sB = sA + offB;
+    T *sC = sA + offC;
+    const int tid = threadIdx.x;
+    const size_t nchunks = (batch + mpc - 1) / mpc;
+    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const size_t first = ch * mpc;
+        const int cnt = (int) ((batch - first) < (size_t) mpc ? (batch - first) : (size_t) mpc);
+        stage_in(sA, A + first * szA, szA * cnt, tid, blockDim.x);
+        stage_in(sB, B + first * szB, szB * cnt, tid, blockDim.x);
+        if (beta != T(0)) stage_in(sC, C + first * szC, szC * cnt, tid, blockDim.x);
+        __syncthreads();
+        for (int w = tid; w < cnt * n; w += blockDim.x) {
+            const int q = w / n, j = w - q * n;
+            const T *a = sA + (size_t) q * szA;
+            const T *b = sB + (size_t) q * szB + (size_t) j * k;
+            T acc[RT];
+#pragma unroll
+            for (int r = 0; r < RT; r++) acc[r] = T(0);
+            for (int kk = 0; kk < k; kk++) {
+                const T bv = b[kk];
+                const T *ac = a + (size_t) kk * m;
+#pragma unroll
+                for (int r = 0; r < RT; r++)
+                    if (r < m) acc[r] = fma(ac[r], bv, acc[r]);
+            }
+            T *c = sC + (size_t) q * szC + (size_t) j * m;
+            if (beta == T(0)) {
+#pragma unroll
+                for (int r = 0; r < RT; r++)
+                    if (r < m) c[r] = alpha * acc[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < RT; r++)
+                    if (r < m) c[r] = alpha * acc[r] + beta * c[r];
+            }
+        }
+        __syncthreads();
+        stage_out(C + first * szC, sC, szC * cnt, tid, blockDim.x);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic tiled kernel: 64x64 tile of one C_i per CTA, 256 threads, 4x4 outputs per thread
+// ------------------------------------------------------------------------------------------
+constexpr int TB = 64; // tile edge
+constexpr int TK = 16; // K panel
+
+template<typename T>
+__global__ void __launch_bounds__(256) k_gemm_tiled(size_t m, size_t n, size_t k, T alpha, const T *__restrict__ A, size_t lda,
+                                                     size_t sA, const T *__restrict__ B, size_t ldb, size_t sB, T beta, T *C,
+                                                     size_t ldc, size_t sC, size_t tiles_m, size_t tiles_n, size_t batch) {
+    __shared__ T As[TK][TB + 4]; // As[kk][row]
+    __shared__ T Bs[TK][TB + 4]; // Bs[kk][col]
+    const size_t tiles = tiles_m * tiles_n;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // tx -> rows, ty -> cols
+    for (size_t t = blockIdx.x; t < tiles * batch; t += gridDim.x) {
+        const size_t b = t / tiles, r = t - b * tiles;
+        const size_t row0 = (r % tiles_m) * TB, col0 = (r / tiles_m) * TB;
+        const T *a = A + b * sA;
+        const T *bb = B + b * sB;
+        T *c = C + b * sC;
+        T acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = T(0);
+        for (size_t k0 = 0; k0 < k; k0 += TK) {
+            // A panel: 64 rows x 16 k ; thread loads 4 elements (consecutive rows => coalesced)
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                int e = threadIdx.x + l * 256;
+                int rr = e & 63, kk = e >> 6;
+                size_t gr = row0 + rr, gk = k0 + kk;
+                As[kk][rr] = (gr < m && gk < k) ? a[gr + gk * lda] : T(0);
+            }
+            // B panel: 16 k x 64 cols ; consecutive threads walk k (contiguous in column-major B)
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                int e = threadIdx.x + l * 256;
+                int kk = e & 15, cc = e >> 4;
+                size_t gk = k0 + kk, gc = col0 + cc;
+                Bs[kk][cc] = (gk < k && gc < n) ? bb[gk + gc * ldb] : T(0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < TK; kk++) {
+                T av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) av[i] = As[kk][tx + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) bv[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            size_t gc = col0 + ty + 16 * j;
+            if (gc >= n) continue;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                size_t gr = row0 + tx + 16 * i;
+                if (gr >= m) continue;
+                T *p = c + gr + gc * ldc;
+                *p = (beta == T(0)) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*p);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp64 tensor-core kernel: 64x64 tile per CTA, 8 warps (4 x 2), each warp 16 x 32 of C
+// = 2 x 4 DMMA tiles (m8n8k4). K panels of 16 staged with cp.async, double buffered.
+// Requires m, n multiples of 64 and k a multiple of 16 (the launcher checks).
+// ------------------------------------------------------------------------------------------
+constexpr int DK = 16;
+constexpr int DLD = 64 + 4; // leading dimension == 4 (mod 16) doubles: the 16 lanes of a half-warp hit 16 distinct bank pairs
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
+                                                    size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
+                                                    double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
+                                                    size_t tiles_n, size_t batch) {
+    // As[buf][kk][row] (A panel, 16 x 64), Bs[buf][col][kk] (B panel stored k-contiguous per column)
+    __shared__ __align__(16) double As[2][DK][DLD];
+    __shared__ __align__(16) double Bs[2][64][DK + 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32; // warp origin inside the tile
+    const int g = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
+    const size_t tiles = tiles_m * tiles_n;
+    for (size_t t = blockIdx.x; t < tiles * batch; t += gridDim.x) {
+        const size_t b = t / tiles, r = t - b * tiles;
+        const size_t row0 = (r % tiles_m) * 64, col0 = (r / tiles_m) * 64;
+        const double *a = A + b * sA + row0;
+        const double *bb = B + b * sB + col0 * ldb;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        auto load_panel = [&](int buf, size_t k0) {
+            // A: 16 columns of 64 rows = 512 double2 ; 256 threads x 2
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                int e = threadIdx.x + l * 256;
+                int rr = (e & 31) * 2, kk = e >> 5;
+                cp_async16(&As[buf][kk][rr], a + rr + (k0 + kk) * lda);
+            }
+            // B: 64 columns of 16 k = 512 double2
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                int e = threadIdx.x + l * 256;
+                int kk = (e & 7) * 2, cc = e >> 3;
+                cp_async16(&Bs[buf][cc][kk], bb + (k0 + kk) + (size_t) cc * ldb);
+            }
+            cp_async_commit();
+        };
+
+        const size_t npan = k / DK;
+        load_panel(0, 0);
+        for (size_t p = 0; p < npan; p++) {
+            const int buf = (int) (p & 1);
+            if (p + 1 < npan) {
+                load_panel(buf ^ 1, (p + 1) * DK);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k4 = 0; k4 < DK; k4 += 4) {
+                double af[2], bf[4];
+#pragma unroll
+                for (int i = 0; i < 2; i++) af[i] = As[buf][k4 + q][wr + 8 * i + g]; // A(row g, k q)
+#pragma unroll
+                for (int j = 0; j < 4; j++) bf[j] = Bs[buf][wc + 8 * j + g][k4 + q]; // B(k q, col g)
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncthreads();
+        }
+        double *c = C + b * sC;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                size_t gr = row0 + wr + 8 * i + g;
+                size_t gc = col0 + wc + 8 * j + 2 * q; // C fragment: row g, cols 2q, 2q+1
+                double *p0 = c + gr + gc * ldc;
+                double *p1 = p0 + ldc;
+                if (beta == 0.0) {
+                    *p0 = alpha * acc[i][j][0];
+                    *p1 = alpha * acc[i][j][1];
+                } else {
+                    *p0 = alpha * acc[i][j][0] + beta * (*p0);
+                    *p1 = alpha * acc[i][j][1] + beta * (*p1);
+                }
+            }
+    }
+}
+
+template<typename T> struct UseDmma { static constexpr bool value = false; };
+template<> struct UseDmma<double> { static constexpr bool value = true; };
+
+inline bool ranges_overlap(const void *p, size_t pbytes, const void *q, size_t qbytes) {
+    uintptr_t a = (uintptr_t) p, b = (uintptr_t) q;
+    return a < b + qbytes && b < a + pbytes;
+}
+
+template<typename T>
+int launch_small(gpub_ctx_t ctx, cudaStream_t stream, int m, int n, int k, T alpha, const T *A, const T *B, T beta, T *C,
+                 size_t batch) {
+    const size_t per_mat = ((size_t) m * k + (size_t) k * n + (size_t) m * n) * sizeof(T);
+    // matrices per chunk: enough columns of work for 256 threads, bounded by ~64 KB of shared memory per CTA
+    int mpc = (int) ((256 + n - 1) / n);
+    const size_t budget = 64 * 1024;
+    if ((size_t) mpc * per_mat > budget) mpc = (int) (budget / per_mat);
+    if (mpc < 1) mpc = 1;
+    if ((size_t) mpc > batch) mpc = (int) batch;
+    const size_t smem = (size_t) mpc * per_mat + 64;
+    const size_t nchunks = gpub_ceil_div(batch, (size_t) mpc);
+    const size_t cap = (size_t) ctx->sm_count * 3;
+    const unsigned grid = (unsigned) (nchunks < cap ? nchunks : cap);
+#define GPUB_SMALL_CASE(RT)                                                                                        \
+    {                                                                                                              \
+        auto kern = k_gemm_small<T, RT>;                                                                           \
+        if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        kern<<<grid, 256, smem, stream>>>(m, n, k, alpha, A, B, beta, C, batch, mpc);                              \
+    }
+    if (m <= 4) GPUB_SMALL_CASE(4)
+    else if (m <= 8) GPUB_SMALL_CASE(8)
+    else if (m <= 16) GPUB_SMALL_CASE(16)
+    else GPUB_SMALL_CASE(32)
+#undef GPUB_SMALL_CASE
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+template<typename T>
+int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha, const T *A, size_t lda, size_t sA,
+                 const T *B, size_t ldb, size_t sB, T beta, T *C, size_t ldc, size_t sC, size_t batch) {
+    if (m == 0 || n == 0 || batch == 0) return GPUB_OK;
+    if (!A || !B || !C) return GPUB_EINVAL;
+    if (lda < m || ldb < k || ldc < m) return GPUB_EINVAL;
+    GPUB_ENTER(ctx, sidx);
+
+    const bool dense = lda == m && ldb == k && ldc == m && (batch == 1 || (sA == m * k && sB == k * n && sC == m * n));
+    if (dense && m <= 32 && n <= 32 && k <= 32 && k > 0 && batch >= 2) {
+        // every operand of a chunk is staged before C is written, so C may alias A or B chunk-wise
+        return launch_small<T>(ctx, stream, (int) m, (int) n, (int) k, alpha, A, B, beta, C, batch);
+    }
+
+    // tiled paths read A/B panels while other CTAs already write C: break aliasing with a scratch copy
+    const size_t spanB = ((batch - 1) * sB + (n - 1) * ldb + k) * sizeof(T);
+    const size_t spanA = ((batch - 1) * sA + (k ? (k - 1) : 0) * lda + m) * sizeof(T);
+    const size_t spanC = ((batch - 1) * sC + (n - 1) * ldc + m) * sizeof(T);
+    T *tmpA = nullptr, *tmpB = nullptr;
+    if (k > 0 && ranges_overlap(C, spanC, B, spanB)) {
+        GPUB_CUDA(cudaMallocAsync((void **) &tmpB, spanB, stream));
+        GPUB_CUDA(cudaMemcpyAsync(tmpB, B, spanB, cudaMemcpyDeviceToDevice, stream));
+        B = tmpB;
+    }
+    if (k > 0 && ranges_overlap(C, spanC, A, spanA)) {
+        GPUB_CUDA(cudaMallocAsync((void **) &tmpA, spanA, stream));
+        GPUB_CUDA(cudaMemcpyAsync(tmpA, A, spanA, cudaMemcpyDeviceToDevice, stream));
+        A = tmpA;
+    }
+
+    const size_t tm = gpub_ceil_div(m, 64), tn = gpub_ceil_div(n, 64);
+    const size_t total = tm * tn * batch;
+    const size_t cap = (size_t) ctx->sm_count * 8;
+    const unsigned grid = (unsigned) (total < cap ? total : cap);
+    bool done = false;
+    if (UseDmma<T>::value) {
+        const bool ok = (m % 64 == 0) && (n % 64 == 0) && (k % DK == 0) && k >= DK && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                        ((((uintptr_t) A) | ((uintptr_t) B)) % 16 == 0) && (sA % 2 == 0) && (sB % 2 == 0);
+        if (ok) {
+            k_gemm_dmma<<<grid, 256, 0, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+                                                  ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+            done = true;
+        }
+    }
+    if (!done)
+        k_gemm_tiled<T><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+    GPUB_LAUNCH_CHECK();
+    if (tmpA) GPUB_CUDA(cudaFreeAsync(tmpA, stream));
+    if (tmpB) GPUB_CUDA(cudaFreeAsync(tmpB, stream));
+    return GPUB_OK;
+}
+
+// P_i = N_i N_i^T : one thread per output element for small n, tiled GEMM-like loop otherwise
+template<typename T>
+__global__ void k_aat(size_t n, const T *__restrict__ N, size_t sN, T *__restrict__ P, size_t sP, size_t batch) {
+    const size_t nn = n * n;
+    for (size_t b = blockIdx.y; b < batch; b += gridDim.y) {
+        const T *nb = N + b * sN;
+        for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t) gridDim.x * blockDim.x) {
+            size_t i = e % n, j = e / n;
+            T acc = 0;
+            for (size_t c = 0; c < n; c++) acc = fma(nb[i + c * n], nb[j + c * n], acc);
+            P[b * sP + e] = acc;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int gpub_gemm_batched_f64(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, double alpha, const double *A, size_t lda,
+                          size_t sA, const double *B, size_t ldb, size_t sB, double beta, double *C, size_t ldc, size_t sC,
+                          size_t batch) {
+    return gemm_batched<double>(ctx, sidx, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+int gpub_gemm_batched_f32(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, float alpha, const float *A, size_t lda,
+                          size_t sA, const float *B, size_t ldb, size_t sB, float beta, float *C, size_t ldc, size_t sC,
+                          size_t batch) {
+    return gemm_batched<float>(ctx, sidx, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+#define GPUB_DEF_AAT(SUF, T)                                                                                         \
+    int gpub_aat_batched_##SUF(gpub_ctx_t ctx, int sidx, size_t n, const T *N, size_t sN, T *P, size_t sP, size_t batch) { \
+        if (n == 0 || batch == 0) return GPUB_OK;                                                                    \
+        if (!N || !P) return GPUB_EINVAL;                                                                            \
+        GPUB_ENTER(ctx, sidx);                                                                                       \
+        unsigned gx = (unsigned) (gpub_ceil_div(n * n, 256) < 4096 ? gpub_ceil_div(n * n, 256) : 4096);              \
+        unsigned gy = (unsigned) (batch < 65535 ? batch : 65535);                                                    \
+        k_aat<T><<<dim3(gx, gy), 256, 0, stream>>>(n, N, sN, P, sP, batch);                                          \
+        GPUB_LAUNCH_CHECK();                                                                                         \
+        return GPUB_OK;                                                                                              \
+    }
+GPUB_DEF_AAT(f64, double)
+GPUB_DEF_AAT(f32, float)
+
+} // extern "C"

@@ -1,0 +1,417 @@
+// Batched Householder QR, application of Q / Q^T, upper-triangular solve and fused least squares.
+// Replaces cusolverDn{D,S}geqrf / ormqr, cublas{D,S}trsm and cublas{D,S}gelsBatched
+// (ref: tensor.cuh:1866-1927, 1929-1995, 1340-1394).
+//
+// Storage follows LAPACK: R on and above the diagonal, the reflector v_j (v_j[j] = 1 implicit) below it,
+// H_j = I - tau_j v_j v_j^T, Q = H_0 H_1 ... H_{n-1}. The sign rule is LAPACK's dlarfg:
+// beta = -sign(alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta), and tau = 0
+// (H = I) when x == 0 -- the rule SVD sign parity depends on (hard part 2).
+//
+//   k_gels_warp<T, M, N> : fused gels for small tall systems (cfg3: 64 x 16 fp32). One matrix per warp,
+//        lane l owns rows l, l+32, ... in registers; [A | b] is factored as one M x (N+1) panel, the
+//        column norms and the v^T A products are warp butterflies, R x = Q^T b is solved in registers.
+//   k_geqrf_cta / k_gels_cta / k_ormqr_cta / k_trsv_cta : any shape, one matrix per CTA, staged in shared
+//        memory when it fits, else in place in global memory (L2 resident).
+#include "common.cuh"
+
+namespace {
+
+constexpr int QT = 256; // threads per CTA for the generic kernels
+
+template<typename T> __device__ __forceinline__ T t_sqrt(T x);
+template<> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template<> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+
+template<typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template<typename T>
+__device__ __forceinline__ T cta_sum(T v, T *s_red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T tot = 0;
+#pragma unroll
+    for (int w = 0; w < QT / 32; w++) tot += s_red[w];
+    __syncthreads();
+    return tot;
+}
+
+// dlarfg on (alpha, xnorm): returns beta, writes tau and the scale 1/(alpha-beta) for x
+template<typename T>
+__device__ __forceinline__ T larfg(T alpha, T xnorm2, T *tau, T *scale) {
+    if (xnorm2 == T(0)) {
+        *tau = T(0);
+        *scale = T(0);
+        return alpha;
+    }
+    T nrm = t_sqrt<T>(alpha * alpha + xnorm2);
+    T beta = alpha >= T(0) ? -nrm : nrm;
+    *tau = (beta - alpha) / beta;
+    *scale = T(1) / (alpha - beta);
+    return beta;
+}
+
+// Factor the first n columns of the m x ncols panel M (leading dimension ld) in place;
+// columns n..ncols-1 (right-hand sides) are only transformed by Q^T.
+template<typename T>
+__device__ void householder_panel(T *M, size_t ld, int m, int n, int ncols, T *tau_out, T *s_red, T *s_bc) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kmax = n < m ? n : m;
+    for (int j = 0; j < kmax; j++) {
+        T *cj = M + (size_t) j * ld;
+        T part = 0;
+        for (int r = j + 1 + tid; r < m; r += QT) part = fma(cj[r], cj[r], part);
+        const T xnorm2 = cta_sum(part, s_red);
+        if (tid == 0) {
+            T tau, scale;
+            T beta = larfg<T>(cj[j], xnorm2, &tau, &scale);
+            cj[j] = beta;
+            s_bc[0] = tau;
+            s_bc[1] = scale;
+            if (tau_out) tau_out[j] = tau;
+        }
+        __syncthreads();
+        const T tau = s_bc[0], scale = s_bc[1];
+        if (tau != T(0)) {
+            for (int r = j + 1 + tid; r < m; r += QT) cj[r] *= scale;
+            __syncthreads();
+            for (int c = j + 1 + warp; c < ncols; c += QT / 32) {
+                T *cc = M + (size_t) c * ld;
+                T w = 0;
+                for (int r = j + 1 + lane; r < m; r += 32) w = fma(cj[r], cc[r], w);
+                w = warp_sum(w) + cc[j];
+                const T tw = tau * w;
+                if (lane == 0) cc[j] -= tw;
+                for (int r = j + 1 + lane; r < m; r += 32) cc[r] = fma(-tw, cj[r], cc[r]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// back substitution R x = y on the leading n x n of M, y = column `rhs` (length >= n), in place
+template<typename T>
+__device__ void upper_solve(const T *M, size_t ld, int n, T *y, int *bad, T *s_bc) {
+    const int tid = threadIdx.x;
+    for (int j = n - 1; j >= 0; j--) {
+        if (tid == 0) {
+            T d = M[j + (size_t) j * ld];
+            if (d == T(0) && bad && *bad == 0) *bad = j + 1;
+            y[j] = y[j] / d;
+            s_bc[0] = y[j];
+        }
+        __syncthreads();
+        const T xj = s_bc[0];
+        const T *cj = M + (size_t) j * ld;
+        for (int r = tid; r < j; r += QT) y[r] = fma(-cj[r], xj, y[r]);
+        __syncthreads();
+    }
+}
+
+template<typename T>
+__device__ __forceinline__ void copy_in(T *dst, size_t ldd, const T *src, size_t lds, int m, int n) {
+    for (size_t e = threadIdx.x; e < (size_t) m * n; e += QT) {
+        int r = (int) (e % m), c = (int) (e / m);
+        dst[r + (size_t) c * ldd] = src[r + (size_t) c * lds];
+    }
+}
+
+// mode 0: geqrf (tau out); mode 1: gels (b is column n, solved in place)
+template<typename T>
+__global__ void __launch_bounds__(QT) k_qr_cta(int m, int n, T *A, size_t lda, size_t sA, T *tau, size_t sTau, T *b, size_t sB,
+                                                int *info, size_t batch, int use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    __shared__ T s_red[QT / 32];
+    __shared__ T s_bc[2];
+    __shared__ int s_bad;
+    const bool gels = b != nullptr;
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *a_g = A + mat * sA;
+        T *b_g = gels ? b + mat * sB : nullptr;
+        T *tau_g = tau ? tau + mat * sTau : nullptr;
+        if (threadIdx.x == 0) s_bad = 0;
+        if (use_smem) {
+            const size_t ld = (size_t) m | 1; // odd leading dimension: column sweeps by different warps spread over banks
+            copy_in(sm, ld, a_g, lda, m, n);
+            if (gels)
+                for (int r = threadIdx.x; r < m; r += QT) sm[r + (size_t) n * ld] = b_g[r];
+            __syncthreads();
+            householder_panel<T>(sm, ld, m, n, gels ? n + 1 : n, tau_g, s_red, s_bc);
+            if (gels) upper_solve<T>(sm, ld, n, sm + (size_t) n * ld, &s_bad, s_bc);
+            copy_in(a_g, lda, sm, ld, m, n);
+            if (gels)
+                for (int r = threadIdx.x; r < m; r += QT) b_g[r] = sm[r + (size_t) n * ld];
+        } else {
+            // in place in global memory (L2 resident); gels never takes this branch, see gels_batched()
+            __syncthreads();
+            householder_panel<T>(a_g, lda, m, n, n, tau_g, s_red, s_bc);
+        }
+        __syncthreads();
+        if (info && threadIdx.x == 0) info[mat] = s_bad;
+        __syncthreads();
+    }
+}
+
+// C <- Q^T C (trans) or Q C: every warp owns whole columns of C, so no CTA-wide synchronisation
+template<typename T>
+__global__ void __launch_bounds__(QT) k_ormqr_cta(int trans, int m, int ncols, int k, const T *__restrict__ A, size_t lda, size_t sA,
+                                                   const T *__restrict__ tau, size_t sTau, T *C, size_t ldc, size_t sC,
+                                                   size_t batch, int col_blocks) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = QT / 32;
+    for (size_t t = blockIdx.x; t < batch * col_blocks; t += gridDim.x) {
+        const size_t mat = t / col_blocks;
+        const int cb = (int) (t % col_blocks);
+        const T *a_g = A + mat * sA;
+        const T *tau_g = tau + mat * sTau;
+        T *c_g = C + mat * sC;
+        for (int c = cb * wpb + warp; c < ncols; c += col_blocks * wpb) {
+            T *cc = c_g + (size_t) c * ldc;
+            for (int jj = 0; jj < k; jj++) {
+                const int j = trans ? jj : k - 1 - jj;
+                const T tj = tau_g[j];
+                if (tj == T(0)) continue;
+                const T *v = a_g + (size_t) j * lda;
+                T w = 0;
+                for (int r = j + 1 + lane; r < m; r += 32) w = fma(v[r], cc[r], w);
+                w = warp_sum(w) + cc[j];
+                const T tw = tj * w;
+                __syncwarp();
+                if (lane == 0) cc[j] -= tw;
+                for (int r = j + 1 + lane; r < m; r += 32) cc[r] = fma(-tw, v[r], cc[r]);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template<typename T>
+__global__ void __launch_bounds__(QT) k_trsv_cta(int n, const T *__restrict__ R, size_t ldr, size_t sR, T *b, size_t sB, size_t batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *x = reinterpret_cast<T *>(smem_raw);
+    __shared__ T s_bc[2];
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *b_g = b + mat * sB;
+        for (int r = threadIdx.x; r < n; r += QT) x[r] = b_g[r];
+        __syncthreads();
+        upper_solve<T>(R + mat * sR, ldr, n, x, nullptr, s_bc);
+        for (int r = threadIdx.x; r < n; r += QT) b_g[r] = x[r];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused gels for small tall systems, one matrix per warp, everything in registers
+// M rows (multiple of 32), N columns; lane l owns rows l + 32*q
+// ------------------------------------------------------------------------------------------
+template<typename T, int M, int N>
+__global__ void __launch_bounds__(128) k_gels_warp(T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
+    constexpr int RQ = M / 32; // rows per lane
+    const int lane = threadIdx.x & 31;
+    const size_t warp_global = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    for (size_t mat = warp_global; mat < batch; mat += nwarps) {
+        T *a_g = A + mat * sA;
+        T *b_g = b + mat * sB;
+        T a[N + 1][RQ];
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int q = 0; q < RQ; q++) a[c][q] = a_g[(size_t) c * M + lane + 32 * q];
+#pragma unroll
+        for (int q = 0; q < RQ; q++) a[N][q] = b_g[lane + 32 * q];
+        int bad = 0;
+        T rdiag[N]; // R(j,j), replicated in every lane
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            // row j lives in lane (j % 32), slot (j / 32)
+            const int jl = j & 31, jq = j >> 5;
+            T part = 0;
+#pragma unroll
+            for (int q = 0; q < RQ; q++) {
+                const int row = lane + 32 * q;
+                const T v = a[j][q];
+                part = fma(row > j ? v : T(0), v, part);
+            }
+            const T xnorm2 = warp_sum(part);
+            const T alpha = __shfl_sync(0xffffffffu, a[j][jq], jl);
+            T tau, scale;
+            const T beta = larfg<T>(alpha, xnorm2, &tau, &scale);
+            rdiag[j] = beta;
+            if (beta == T(0) && bad == 0) bad = j + 1;
+            // v = x * scale below the diagonal, 1 on it, 0 above
+            T v[RQ];
+#pragma unroll
+            for (int q = 0; q < RQ; q++) {
+                const int row = lane + 32 * q;
+                v[q] = row > j ? a[j][q] * scale : (row == j ? T(1) : T(0));
+                if (row > j) a[j][q] = v[q];
+                else if (row == j) a[j][q] = beta;
+            }
+            if (tau != T(0)) {
+#pragma unroll
+                for (int c = j + 1; c <= N; c++) {
+                    T w = 0;
+#pragma unroll
+                    for (int q = 0; q < RQ; q++) w = fma(v[q], a[c][q], w);
+                    w = warp_sum(w);
+                    const T tw = tau * w;
+#pragma unroll
+                    for (int q = 0; q < RQ; q++) a[c][q] = fma(-tw, v[q], a[c][q]);
+                }
+            }
+        }
+        // back substitution on R (rows 0..N-1 of the columns; row r in lane r%32, slot r/32)
+#pragma unroll
+        for (int j = N - 1; j >= 0; j--) {
+            const int jl = j & 31, jq = j >> 5;
+            T xj = __shfl_sync(0xffffffffu, a[N][jq], jl) / rdiag[j];
+#pragma unroll
+            for (int q = 0; q < RQ; q++) {
+                const int row = lane + 32 * q;
+                if (row == j) a[N][q] = xj;
+                else if (row < j) a[N][q] = fma(-a[j][q], xj, a[N][q]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N; c++)
+#pragma unroll
+            for (int q = 0; q < RQ; q++) a_g[(size_t) c * M + lane + 32 * q] = a[c][q];
+#pragma unroll
+        for (int q = 0; q < RQ; q++) b_g[lane + 32 * q] = a[N][q];
+        if (info && lane == 0) info[mat] = bad;
+    }
+}
+
+template<typename T>
+size_t qr_smem_bytes(size_t m, size_t n, bool gels) {
+    return ((m | 1) * (n + (gels ? 1 : 0))) * sizeof(T);
+}
+
+template<typename T>
+int geqrf_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda, size_t sA, T *tau, size_t sTau, size_t batch) {
+    if (m == 0 || n == 0 || batch == 0) return GPUB_OK;
+    if (!A || !tau || lda < m) return GPUB_EINVAL;
+    if (m > (size_t) INT32_MAX || n > (size_t) INT32_MAX) return GPUB_ENOTSUP;
+    GPUB_ENTER(ctx, sidx);
+    const size_t bytes = qr_smem_bytes<T>(m, n, false);
+    const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 2048 ? 1 : 0;
+    const size_t smem = use_smem ? bytes : 0;
+    if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(k_qr_cta<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t cap = (size_t) ctx->sm_count * 4;
+    const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+    k_qr_cta<T><<<grid, QT, smem, stream>>>((int) m, (int) n, A, lda, sA, tau, sTau, nullptr, 0, nullptr, batch, use_smem);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+template<typename T>
+int ormqr_batched(gpub_ctx_t ctx, int sidx, int trans, size_t m, size_t ncols, size_t k, const T *A, size_t lda, size_t sA,
+                  const T *tau, size_t sTau, T *C, size_t ldc, size_t sC, size_t batch) {
+    if (m == 0 || ncols == 0 || k == 0 || batch == 0) return GPUB_OK;
+    if (!A || !tau || !C || lda < m || ldc < m || k > m) return GPUB_EINVAL;
+    GPUB_ENTER(ctx, sidx);
+    // split the columns of C over several CTAs when the batch alone cannot fill the GPU
+    size_t col_blocks = 1;
+    const size_t wpb = QT / 32;
+    const size_t target = (size_t) ctx->sm_count * 4;
+    if (batch < target) {
+        col_blocks = gpub_ceil_div(target, batch);
+        const size_t maxb = gpub_ceil_div(ncols, wpb);
+        if (col_blocks > maxb) col_blocks = maxb;
+    }
+    const size_t total = batch * col_blocks;
+    const size_t cap = (size_t) ctx->sm_count * 8;
+    const unsigned grid = (unsigned) (total < cap ? total : cap);
+    k_ormqr_cta<T><<<grid, QT, 0, stream>>>(trans, (int) m, (int) ncols, (int) k, A, lda, sA, tau, sTau, C, ldc, sC, batch,
+                                            (int) col_blocks);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+template<typename T>
+int trsv_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *R, size_t ldr, size_t sR, T *b, size_t sB, size_t batch) {
+    if (n == 0 || batch == 0) return GPUB_OK;
+    if (!R || !b || ldr < n) return GPUB_EINVAL;
+    GPUB_ENTER(ctx, sidx);
+    const size_t smem = n * sizeof(T);
+    if (smem > (size_t) ctx->max_smem_optin - 1024) return GPUB_ENOTSUP;
+    if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(k_trsv_cta<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t cap = (size_t) ctx->sm_count * 8;
+    const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+    k_trsv_cta<T><<<grid, QT, smem, stream>>>((int) n, R, ldr, sR, b, sB, batch);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+template<typename T, int M, int N>
+int launch_gels_warp(gpub_ctx_t ctx, cudaStream_t stream, T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
+    const size_t want = gpub_ceil_div(batch, 4);
+    const size_t cap = (size_t) ctx->sm_count * 16;
+    const unsigned grid = (unsigned) (want < cap ? want : cap);
+    k_gels_warp<T, M, N><<<grid, 128, 0, stream>>>(A, sA, b, sB, info, batch);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+template<typename T>
+int gels_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda, size_t sA, T *b, size_t sB, int *info,
+                 size_t batch) {
+    if (m == 0 || batch == 0) return GPUB_OK;
+    if (!A || !b || lda < m || n > m) return GPUB_EINVAL;
+    GPUB_ENTER(ctx, sidx);
+    if (n == 0) return GPUB_OK;
+    if (lda == m) {
+        if (m == 64 && n == 16) return launch_gels_warp<T, 64, 16>(ctx, stream, A, sA, b, sB, info, batch);
+        if (m == 32 && n == 16) return launch_gels_warp<T, 32, 16>(ctx, stream, A, sA, b, sB, info, batch);
+        if (m == 32 && n == 8) return launch_gels_warp<T, 32, 8>(ctx, stream, A, sA, b, sB, info, batch);
+    }
+    const size_t bytes = qr_smem_bytes<T>(m, n, true);
+    if (bytes > (size_t) ctx->max_smem_optin - 2048) {
+        // too large for one CTA's shared memory: geqrf in place, then Q^T b, then the triangular solve,
+        // with tau kept in a stream-ordered scratch buffer
+        T *tau = nullptr;
+        GPUB_CUDA(cudaMallocAsync((void **) &tau, n * batch * sizeof(T), stream));
+        const size_t cap = (size_t) ctx->sm_count * 4;
+        const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+        k_qr_cta<T><<<grid, QT, 0, stream>>>((int) m, (int) n, A, lda, sA, tau, n, nullptr, 0, nullptr, batch, 0);
+        GPUB_LAUNCH_CHECK();
+        int e = ormqr_batched<T>(ctx, sidx, 1, m, 1, n, A, lda, sA, tau, n, b, m, sB, batch);
+        if (e) return e;
+        e = trsv_batched<T>(ctx, sidx, n, A, lda, sA, b, sB, batch);
+        if (e) return e;
+        if (info) GPUB_CUDA(cudaMemsetAsync(info, 0, batch * sizeof(int), stream));
+        GPUB_CUDA(cudaFreeAsync(tau, stream));
+        return GPUB_OK;
+    }
+    if (bytes > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(k_qr_cta<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+    const size_t cap = (size_t) ctx->sm_count * 4;
+    const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+    k_qr_cta<T><<<grid, QT, bytes, stream>>>((int) m, (int) n, A, lda, sA, nullptr, 0, b, sB, info, batch, 1);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gpub_geqrf_batched_f64(gpub_ctx_t c, int s, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sT, size_t b) { return geqrf_batched<double>(c, s, m, n, A, lda, sA, tau, sT, b); }
+int gpub_geqrf_batched_f32(gpub_ctx_t c, int s, size_t m, size_t n, float *A, size_t lda, size_t sA, float *tau, size_t sT, size_t b) { return geqrf_batched<float>(c, s, m, n, A, lda, sA, tau, sT, b); }
+
+int gpub_ormqr_batched_f64(gpub_ctx_t c, int s, int trans, size_t m, size_t nc, size_t k, const double *A, size_t lda, size_t sA, const double *tau, size_t sT, double *C, size_t ldc, size_t sC, size_t b) { return ormqr_batched<double>(c, s, trans, m, nc, k, A, lda, sA, tau, sT, C, ldc, sC, b); }
+int gpub_ormqr_batched_f32(gpub_ctx_t c, int s, int trans, size_t m, size_t nc, size_t k, const float *A, size_t lda, size_t sA, const float *tau, size_t sT, float *C, size_t ldc, size_t sC, size_t b) { return ormqr_batched<float>(c, s, trans, m, nc, k, A, lda, sA, tau, sT, C, ldc, sC, b); }
+
+int gpub_trsv_upper_batched_f64(gpub_ctx_t c, int s, size_t n, const double *R, size_t ldr, size_t sR, double *b, size_t sB, size_t bt) { return trsv_batched<double>(c, s, n, R, ldr, sR, b, sB, bt); }
+int gpub_trsv_upper_batched_f32(gpub_ctx_t c, int s, size_t n, const float *R, size_t ldr, size_t sR, float *b, size_t sB, size_t bt) { return trsv_batched<float>(c, s, n, R, ldr, sR, b, sB, bt); }
+
+int gpub_gels_batched_f64(gpub_ctx_t c, int s, size_t m, size_t n, double *A, size_t lda, size_t sA, double *b, size_t sB, int *info, size_t bt) { return gels_batched<double>(c, s, m, n, A, lda, sA, b, sB, info, bt); }
+int gpub_gels_batched_f32(gpub_ctx_t c, int s, size_t m, size_t n, float *A, size_t lda, size_t sA, float *b, size_t sB, int *info, size_t bt) { return gels_batched<float>(c, s, m, n, A, lda, sA, b, sB, info, bt); }
+
+} // extern "C"
