@@ -1,0 +1,294 @@
+"""GPU: the CUDA path, called through the C ABI (include/gputils_b200.h), against the CPU oracle on the same
+seeded inputs. Tolerances (BASELINE.md / north_star): relative Frobenius error <= 1e-12 for fp64 and <= 1e-5
+for fp32; exact equality where the arithmetic is exact (integer-valued data, copies, transposes, counts)."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float64, np.float32]
+
+
+def dev(a):
+    from gputils_b200 import capi
+    return capi.from_numpy_batch(a)
+
+
+def host(t):
+    from gputils_b200 import capi
+    return capi.to_numpy_batch(t)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,k,batch", [
+    (8, 8, 8, 4096),          # BASELINE config 1
+    (2, 2, 3, 3), (3, 2, 3, 5), (1, 1, 1, 7), (5, 7, 3, 33), (4, 4, 4, 1000), (16, 16, 16, 257), (32, 32, 32, 129),
+    (7, 1, 7, 10),            # mat-vec, the example/main.cu shape class
+    (33, 17, 9, 4), (64, 64, 64, 9), (128, 128, 128, 3), (100, 37, 51, 2), (64, 64, 64, 1), (200, 1, 300, 1),
+])
+def test_gemm_batched(gpu_ctx, oracle, dt, m, n, k, batch):
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(1000 + m + 7 * n + 13 * k)
+    A = rng.uniform(-1, 1, (batch, m, k)).astype(dt); B = rng.uniform(-1, 1, (batch, k, n)).astype(dt)
+    C0 = rng.uniform(-1, 1, (batch, m, n)).astype(dt)
+    dC = dev(C0)
+    capi.gemm_batched(gpu_ctx, dC, dev(A), dev(B), 1.0, 0.0)
+    assert rel_err(host(dC), oracle.gemm_batched(A, B)) <= TOL[np.dtype(dt)]
+    dC = dev(C0)
+    capi.gemm_batched(gpu_ctx, dC, dev(A), dev(B), -0.5, 2.0)
+    assert rel_err(host(dC), oracle.gemm_batched(A, B, C0, -0.5, 2.0)) <= TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gemm_exact_on_integer_data_and_empty_batch(gpu_ctx, golden, dt):
+    import torch
+    from conftest import mats, with_layout
+    from gputils_b200 import capi
+    g = golden["addAB"]
+    A, B, C = (mats(with_layout(g, k), dt) for k in "ABC")
+    dC = torch.zeros((3, 2, 2), dtype=dev(A).dtype, device="cuda")
+    capi.gemm_batched(gpu_ctx, dC, dev(A), dev(B))
+    assert np.array_equal(host(dC), C)
+    empty = torch.zeros((0, 2, 2), dtype=dC.dtype, device="cuda")
+    capi.gemm_batched(gpu_ctx, empty, torch.zeros((0, 3, 2), dtype=dC.dtype, device="cuda"), torch.zeros((0, 2, 3), dtype=dC.dtype, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,batch", [(7, 1), (7, 64), (32, 100), (100, 3), (1024, 2)])
+def test_gemm_output_aliasing_rhs(gpu_ctx, dt, n, batch):
+    """Nullspace::project calls b.addAB(P, b): C aliases B (ref: tensor.cuh:2084)."""
+    from gputils_b200 import capi
+    rng = np.random.default_rng(n)
+    P = rng.uniform(-1, 1, (batch, n, n)).astype(dt); b = rng.uniform(-1, 1, (batch, n, 1)).astype(dt)
+    db = dev(b)
+    capi.gemm_batched(gpu_ctx, db, dev(P), db)
+    assert rel_err(host(db), P.astype(np.float64) @ b.astype(np.float64)) <= 10 * TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,batch", [(1, 5), (2, 9), (3, 2), (4, 1000), (5, 77), (8, 1000), (13, 50), (16, 513), (20, 33),
+                                     (32, 1000), (32, 1), (33, 7), (64, 10), (100, 3), (128, 4), (200, 2)])
+def test_potrf_potrs(gpu_ctx, oracle, dt, n, batch):
+    import torch
+    from gputils_b200 import capi
+    A = oracle.fill_spd_batched(n, batch, float(n), 0x5EED0002 + n, dt)
+    b = oracle.fill_uniform(batch * n, -1.0, 1.0, 0x5EED0102 + n, dt).reshape(batch, n, 1)
+    dA = dev(A); db = dev(b)
+    info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    capi.potrf_batched(gpu_ctx, dA, info)
+    L = host(dA)
+    Lo, info_o = oracle.potrf_batched(A)
+    assert np.array_equal(info.cpu().numpy(), info_o) and not info_o.any()
+    assert np.array_equal(np.triu(L, 1), np.triu(A, 1)), "strict upper triangle must stay untouched"
+    assert rel_err(np.tril(L), np.tril(Lo)) <= TOL[np.dtype(dt)]
+    Lt = np.tril(L).astype(np.float64)
+    assert rel_err(Lt @ Lt.transpose(0, 2, 1), A) <= TOL[np.dtype(dt)]
+    capi.potrs_batched(gpu_ctx, dA, db)
+    x = host(db)
+    assert rel_err(x, oracle.potrs_batched(Lo, b)) <= 20 * TOL[np.dtype(dt)]
+    assert rel_err(A.astype(np.float64) @ x, b) <= 20 * TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n", [3, 8, 32, 40])
+def test_potrf_reports_first_bad_pivot(gpu_ctx, oracle, dt, n):
+    import torch
+    from gputils_b200 import capi
+    A = oracle.fill_spd_batched(n, 6, float(n), 11, dt)
+    A[1, n // 2, n // 2] = -1.0          # leading minor n//2+1 not positive
+    A[4] = 0.0                           # zero matrix: fails at pivot 1
+    dA = dev(A)
+    info = torch.zeros(6, dtype=torch.int32, device="cuda")
+    capi.potrf_batched(gpu_ctx, dA, info)
+    _, info_o = oracle.potrf_batched(A)
+    assert info.cpu().tolist() == info_o.tolist() == [0, n // 2 + 1, 0, 0, 1, 0]
+    good = [0, 2, 3, 5]
+    Lo, _ = oracle.potrf_batched(A[good])
+    assert rel_err(np.tril(host(dA)[good]), np.tril(Lo)) <= TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,batch", [(2, 2, 3), (64, 16, 1000), (64, 16, 3), (32, 16, 65), (32, 8, 100), (20, 3, 5), (4, 3, 1),
+                                       (100, 30, 4), (300, 40, 2), (16, 16, 20), (2000, 24, 2)])
+def test_gels_batched(gpu_ctx, oracle, dt, m, n, batch):
+    import torch
+    from gputils_b200 import capi
+    A = oracle.fill_uniform(batch * m * n, -1.0, 1.0, 0x5EED0003, dt).reshape(batch, n, m).transpose(0, 2, 1).copy()
+    b = oracle.fill_uniform(batch * m, -1.0, 1.0, 0x5EED0103, dt).reshape(batch, m, 1)
+    dA = dev(A); db = dev(b)
+    info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    capi.gels_batched(gpu_ctx, dA, db, info)
+    qr_o, xb_o, info_o = oracle.gels_batched(A, b)
+    assert not info.cpu().numpy().any() and not info_o.any()
+    tol = 50 * TOL[np.dtype(dt)]
+    xb = host(db)
+    assert rel_err(xb[:, :n], xb_o[:, :n]) <= tol           # the solution
+    assert rel_err(xb, xb_o) <= tol                          # ... and the Q^T b tail the reference leaves behind
+    assert rel_err(host(dA), qr_o) <= tol                    # A overwritten by the same QR factors
+    x64 = xb[:, :n].astype(np.float64); A64 = A.astype(np.float64)
+    grad = A64.transpose(0, 2, 1) @ (A64 @ x64 - b)          # normal equations
+    assert np.linalg.norm(grad) <= tol * np.linalg.norm(A64) * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,batch", [(4, 3, 1), (20, 3, 1), (64, 16, 9), (128, 128, 2), (300, 20, 3), (1024, 128, 2)])
+def test_geqrf_ormqr_trsv(gpu_ctx, oracle, dt, m, n, batch):
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(m + n)
+    A = rng.uniform(-100, 100, (batch, m, n)).astype(dt)
+    b = rng.uniform(-1, 1, (batch, m, 1)).astype(dt)
+    dA = dev(A)
+    tau = torch.zeros((batch, n), dtype=dA.dtype, device="cuda")
+    capi.geqrf_batched(gpu_ctx, dA, tau)
+    qr_o, tau_o = oracle.geqrf_batched(A)
+    tol = 100 * TOL[np.dtype(dt)]
+    assert rel_err(host(dA), qr_o) <= tol and rel_err(tau.cpu().numpy(), tau_o) <= tol
+    # Q from the reflectors: Q R = A  (QRFactoriser::getQR, tensor.cuh:1929-1995)
+    eye = np.tile(np.eye(m, n, dtype=dt), (batch, 1, 1))
+    dQ = dev(eye)
+    capi.ormqr_batched(gpu_ctx, False, dA, tau, dQ)
+    Q = host(dQ).astype(np.float64)
+    R = np.triu(host(dA)[:, :n, :]).astype(np.float64)
+    assert rel_err(Q @ R, A) <= tol
+    assert np.abs(Q.transpose(0, 2, 1) @ Q - np.eye(n)).max() <= tol * 10
+    # least squares: Q^T b then R x = (Q^T b)[0:n]  (QRFactoriser::leastSquares, tensor.cuh:1891-1927)
+    db = dev(b)
+    capi.ormqr_batched(gpu_ctx, True, dA, tau, db)
+    assert rel_err(host(db), oracle.ormqr_batched(True, qr_o, tau_o, b)) <= tol
+    capi.trsv_upper_batched(gpu_ctx, dA, n, m, m * n, db, m, batch)
+    x = host(db)[:, :n].astype(np.float64)
+    xr = np.stack([np.linalg.lstsq(A[i].astype(np.float64), b[i].astype(np.float64), rcond=None)[0] for i in range(batch)])
+    assert rel_err(x, xr) <= 1000 * TOL[np.dtype(dt)]
+
+
+def _subspace_gap(U1, U2):
+    return np.abs(U1 @ U1.T - U2 @ U2.T).max()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,batch,want_u", [(3, 2, 3, True), (8, 3, 4, True), (4, 3, 3, False), (3, 3, 5, True), (64, 16, 40, True),
+                                              (64, 32, 3, True), (200, 20, 3, True), (200, 20, 3, False), (500, 8, 2, True)])
+def test_gesvd_batched(gpu_ctx, oracle, dt, m, n, batch, want_u):
+    from gputils_b200 import capi
+    rng = np.random.default_rng(7 * m + n)
+    A = rng.uniform(-1, 1, (batch, m, n)).astype(dt)
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), want_u)
+    So, Uo, Vto = oracle.gesvd_batched(A.astype(np.float64), want_u)
+    tol = 100 * TOL[np.dtype(dt)]
+    assert not info.cpu().numpy().any()
+    Sn = S.cpu().numpy().astype(np.float64)
+    assert np.all(np.diff(Sn, axis=1) <= 0) and np.all(Sn >= 0)
+    assert rel_err(Sn, So) <= tol
+    Vn = host(Vt).astype(np.float64)
+    assert np.abs(Vn @ Vn.transpose(0, 2, 1) - np.eye(n)).max() <= tol
+    # singular vectors up to sign (singular values are distinct with probability one)
+    assert np.abs(np.abs(Vn) - np.abs(Vto)).max() <= 1e4 * tol
+    if want_u:
+        Un = host(U).astype(np.float64)
+        assert np.abs(Un.transpose(0, 2, 1) @ Un - np.eye(m)).max() <= tol
+        assert rel_err(Un[:, :, :n] * Sn[:, None, :] @ Vn, A) <= tol
+        for i in range(batch):   # orthogonal complement spans the same subspace as LAPACK's
+            assert _subspace_gap(Un[i][:, n:], Uo[i][:, n:]) <= 1e3 * tol
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gesvd_rank_deficient_and_rank_count(gpu_ctx, oracle, golden, dt):
+    import torch
+    from conftest import mats, with_layout
+    from gputils_b200 import capi
+    A = mats(with_layout(golden["svd_rank"], "A"), dt)
+    S, _, _, info = capi.gesvd_batched(gpu_ctx, dev(A), False)
+    count = torch.zeros(3, dtype=torch.int32, device="cuda")
+    eps = 1e-10 if dt == np.float64 else 1e-4
+    gpu_ctx.call("count_gt_batched", S, capi._p(S), 3, 3, eps, capi._p(count), 3)
+    assert count.cpu().tolist() == golden["svd_rank"]["rank"]
+    gpu_ctx.call("count_gt_batched", S, capi._p(S), 3, 3, eps, capi._p(count), 3)   # accumulates, like the reference kernel
+    assert count.cpu().tolist() == [2 * r for r in golden["svd_rank"]["rank"]]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n", [1, 5, 1000, 4097, 1_000_003])
+def test_reductions_and_elementwise(gpu_ctx, oracle, dt, n):
+    import torch
+    from gputils_b200 import capi
+    x = oracle.fill_uniform(n + 3, -1.0, 1.0, 21, dt); y = oracle.fill_uniform(n + 3, -1.0, 1.0, 22, dt)
+    for off in (0, 1):                      # off = 1: a view that is not 16-byte aligned (slices do this)
+        dx = torch.from_numpy(x).cuda()[off:off + n]; dy = torch.from_numpy(y).cuda()[off:off + n]
+        xs, ys = x[off:off + n], y[off:off + n]
+        tol = 10 * TOL[np.dtype(dt)]
+        assert abs(capi.reduce_scalar(gpu_ctx, "nrm2", dx) - oracle.nrm2(xs)) <= tol * oracle.nrm2(xs)
+        assert abs(capi.reduce_scalar(gpu_ctx, "asum", dx) - oracle.asum(xs)) <= tol * oracle.asum(xs)
+        assert abs(capi.reduce_scalar(gpu_ctx, "dot", dx, dy) - oracle.dot(xs, ys)) <= tol * np.sqrt(n)
+        v, i = capi.reduce_scalar(gpu_ctx, "amax_abs", dx)
+        assert v == np.abs(xs).max() and i == int(np.abs(xs).argmax())
+        v, i = capi.reduce_scalar(gpu_ctx, "amin_abs", dx)
+        assert v == np.abs(xs).min() and i == int(np.abs(xs).argmin())
+        dz = dy.clone()
+        gpu_ctx.call("axpy", dz, n, -1.0, capi._p(dx), capi._p(dz))
+        assert np.array_equal(dz.cpu().numpy(), ys - xs)
+        gpu_ctx.call("scal", dz, n, 3.0, capi._p(dz))
+        assert np.array_equal(dz.cpu().numpy(), dt(3.0) * (ys - xs))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,batch", [(3, 2, 2), (1, 9, 4), (17, 33, 5), (64, 16, 100), (128, 1024, 3)])
+def test_transpose_batched(gpu_ctx, dt, m, n, batch):
+    from gputils_b200 import capi
+    rng = np.random.default_rng(m * n)
+    A = rng.uniform(-1, 1, (batch, m, n)).astype(dt)
+    At = capi.transpose_batched(gpu_ctx, dev(A))
+    assert np.array_equal(host(At), A.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_nullspace_pack_and_projector(gpu_ctx, dt):
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(5)
+    n, batch = 6, 7
+    U = rng.uniform(-1, 1, (batch, n, n)).astype(dt)
+    rank = np.array([0, 1, 3, 6, 5, 2, 6], dtype=np.int32)
+    dU = dev(U); dN = torch.empty_like(dU); dP = torch.empty_like(dU)
+    dr = torch.from_numpy(rank).cuda()
+    gpu_ctx.call("nullspace_pack_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, batch)
+    gpu_ctx.call("aat_batched", dU, n, capi._p(dN), n * n, capi._p(dP), n * n, batch)
+    N = host(dN)
+    for i in range(batch):
+        nul = n - rank[i]
+        assert np.array_equal(N[i][:, :nul], U[i][:, n - nul:]) and not N[i][:, nul:].any()
+    assert rel_err(host(dP), N.astype(np.float64) @ N.astype(np.float64).transpose(0, 2, 1)) <= TOL[np.dtype(dt)]
+    assert not host(dP)[3].any() and not host(dP)[6].any()          # full rank -> exactly zero projector
+
+
+def test_generators_match_the_numpy_mirror(gpu_ctx, oracle):
+    import torch
+    from gputils_b200 import capi
+    x = torch.empty(10_001, dtype=torch.float64, device="cuda")
+    capi.fill_uniform(gpu_ctx, x, -1.0, 1.0, 0x5EED0001)
+    assert np.array_equal(x.cpu().numpy(), oracle.fill_uniform(10_001, -1.0, 1.0, 0x5EED0001))
+    A = torch.empty((5, 8, 8), dtype=torch.float64, device="cuda")
+    capi.fill_spd_batched(gpu_ctx, A, 8.0, 99)
+    assert rel_err(host(A), oracle.fill_spd_batched(8, 5, 8.0, 99)) <= 1e-15
+
+
+def test_padded_strides_are_accepted(gpu_ctx, oracle):
+    """The C ABI takes explicit leading dimensions and batch strides (128-byte aligned padded layouts)."""
+    import torch
+    from gputils_b200 import capi
+    n, batch, ld, stride = 5, 11, 8, 48          # ld 8, 48 doubles = 384 B per matrix
+    A = oracle.fill_spd_batched(n, batch, 5.0, 3)
+    buf = torch.full((batch, stride), 777.0, dtype=torch.float64, device="cuda")
+    for i in range(batch):
+        buf[i, : ld * n].view(n, ld)[:, :n] = torch.from_numpy(A[i].T.copy()).cuda()
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    gpu_ctx.call("potrf_batched", buf, n, capi._p(buf), ld, stride, capi._p(info), batch)
+    Lo, _ = oracle.potrf_batched(A)
+    out = buf.cpu().numpy()
+    for i in range(batch):
+        L = out[i, : ld * n].reshape(n, ld)[:, :n].T
+        assert rel_err(np.tril(L), np.tril(Lo[i])) <= 1e-13
+        assert np.all(out[i, ld * n:] == 777.0) and np.all(out[i, : ld * n].reshape(n, ld)[:, n:] == 777.0)
