@@ -18,7 +18,13 @@ REPO = ROOT.parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
 OBJDIR = LIBDIR / "obj"
-LIB = LIBDIR / "libgputils_b200.so"
+# tuning aid: GPUB_VARIANT=name + GPUB_EXTRA_NVCC_FLAGS="-DX=.." builds lib/variants/libgputils_b200_<name>.so
+VARIANT = os.environ.get("GPUB_VARIANT", "")
+if VARIANT:
+    OBJDIR = LIBDIR / "variants" / ("obj_" + VARIANT)
+    LIB = LIBDIR / "variants" / f"libgputils_b200_{VARIANT}.so"
+else:
+    LIB = LIBDIR / "libgputils_b200.so"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(REPO / "include"), "-I", str(CSRC)]
@@ -44,7 +50,7 @@ def _compile(src: str, force: bool, verbose: bool) -> Path:
     srcp = CSRC / src
     if not force and obj.exists() and obj.stat().st_mtime > max(srcp.stat().st_mtime, _newest_header()):
         return obj
-    cmd = [nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), "-c", str(srcp), "-o", str(obj)]
+    cmd = [nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), *os.environ.get("GPUB_EXTRA_NVCC_FLAGS", "").split(), "-c", str(srcp), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

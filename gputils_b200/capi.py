@@ -16,7 +16,7 @@ from pathlib import Path
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgputils_b200.so"
+_LIB_PATH = Path(os.environ.get("GPUB_LIB") or (Path(__file__).resolve().parent / "lib" / "libgputils_b200.so"))  # GPUB_LIB: tuning variants only
 
 
 class GpubError(RuntimeError):

@@ -24,60 +24,77 @@ namespace {
 
 template<typename T> __device__ __forceinline__ T fast_rsqrt(T d);
 template<> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
-    // rsqrt() is ~1 ulp; one Newton step on (d, r) makes s = d*r a correctly rounded-quality sqrt
-    double r = rsqrt(d);
-    double e = fma(-d * r, r, 1.0); // 1 - d r^2
-    return fma(0.5 * r, e, r);
+    // MUFU.RSQ64H seed (~2^-22) + two Newton steps y <- y + y (1/2 - (d/2) y^2): ~1 ulp, no special-case
+    // branch or slow-path call (d <= 0 is reported through info; the result is then NaN / inf by design)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    return y;
 }
 template<> __device__ __forceinline__ float fast_rsqrt<float>(float d) {
     float r = rsqrtf(d);
-    float e = fmaf(-d * r, r, 1.0f);
-    return fmaf(0.5f * r, e, r);
+    return fmaf(0.5f * r, fmaf(-d * r, r, 1.0f), r); // one Newton step: rsqrtf alone is ~2 ulp
 }
 
 // ------------------------------------------------------------------------------------------
 // potrf, n <= 32: NP lanes per matrix
+// Control flow is uniform across the CTA (tail groups redo the last matrix with stores masked) and the
+// padding rows/columns of a group with n < NP are an identity block, so the NP column steps run
+// unconditionally: the whole factorisation is one basic block that ptxas can software-pipeline
+// (the pivot of column j+1 is broadcast and its rsqrt started while column j's update is still issuing).
 // ------------------------------------------------------------------------------------------
-template<typename T, int NP>
-__global__ void __launch_bounds__(256) k_potrf_group(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
-    constexpr int GROUPS = 256 / NP;
-    __shared__ __align__(16) T s_col[GROUPS][NP];
+#ifndef GPUB_POTRF_THREADS
+#define GPUB_POTRF_THREADS 128
+#endif
+#ifndef GPUB_POTRF_MINB
+#define GPUB_POTRF_MINB 5
+#endif
+
+// DENSE: n == NP and lda == NP, so every load/store offset is an immediate.
+template<typename T, int NP, bool DENSE>
+__global__ void __launch_bounds__(GPUB_POTRF_THREADS, GPUB_POTRF_MINB)
+k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batch) {
+    const size_t lda = DENSE ? (size_t) NP : lda_rt;
+    constexpr int GROUPS = GPUB_POTRF_THREADS / NP;
+    __shared__ __align__(16) T s_col[2][GROUPS][NP];
     const int grp = threadIdx.x / NP;
     const int i = threadIdx.x % NP; // row owned by this lane
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned gmask = (NP == 32) ? 0xffffffffu : (((1u << NP) - 1u) << (lane & ~(unsigned) (NP - 1)));
     const size_t ngroups = (size_t) gridDim.x * GROUPS;
-    const bool row_ok = i < n;
-    T *col = s_col[grp];
+    const size_t iters = (batch + ngroups - 1) / ngroups;
+    const bool row_ok = DENSE || i < n;
 
-    for (size_t mat = (size_t) blockIdx.x * GROUPS + grp; mat < batch; mat += ngroups) {
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * ngroups + (size_t) blockIdx.x * GROUPS + grp;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
         T *a_g = A + mat * strideA;
         T a[NP];
-        // lower triangle only: lane i needs columns 0..i
+        // lower triangle only: lane i needs columns 0..i; everything else is an identity pattern
 #pragma unroll
         for (int c = 0; c < NP; c++) a[c] = (row_ok && c <= i) ? a_g[i + (size_t) c * lda] : T(c == i ? 1 : 0);
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < NP; j++) {
-            if (j < n) { // warp-uniform
-                const T d = __shfl_sync(gmask, a[j], j, NP);
-                if (!(d > T(0)) && bad == 0) bad = j + 1;
-                const T r = fast_rsqrt<T>(d);
-                const T l = a[j] * r; // lane j: sqrt(d); lanes below: L(i,j)
-                a[j] = l;
-                col[i] = l;
-                __syncwarp(gmask);
+            const T d = __shfl_sync(0xffffffffu, a[j], j, NP);
+            if (!(d > T(0)) && bad == 0) bad = j + 1;
+            const T r = fast_rsqrt<T>(d);
+            const T l = a[j] * r; // lane j: sqrt(d); lanes below: L(i,j); lanes above: 0
+            a[j] = l;
+            T *col = s_col[j & 1][grp];
+            col[i] = l;
+            __syncwarp();
 #pragma unroll
-                for (int c = j + 1; c < NP; c++) a[c] = fma(-l, col[c], a[c]);
-                __syncwarp(gmask);
-            }
+            for (int c = j + 1; c < NP; c++) a[c] = fma(-l, col[c], a[c]);
         }
-        if (row_ok) {
+        if (row_ok && live) {
 #pragma unroll
             for (int c = 0; c < NP; c++)
                 if (c <= i) a_g[i + (size_t) c * lda] = a[c];
         }
-        if (i == 0) info[mat] = bad;
+        if (i == 0 && live) info[mat] = bad;
+        __syncwarp();
     }
 }
 
@@ -133,61 +150,72 @@ __global__ void __launch_bounds__(256) k_potrf_cta(int n, T *A, size_t lda, size
 }
 
 // ------------------------------------------------------------------------------------------
-// potrs, n <= 32
+// potrs, n <= 32: NP lanes per matrix.
+// With D = diag(L) and the row-scaled factor Lb = D^-1 L (unit diagonal, Lb(i,j) = L(i,j) / L(i,i)):
+//     L y = b      <=>  Lb y = D^-1 b          (forward, row layout:    lane i owns row i of Lb)
+//     L^T z = y    <=>  Lb^T (D z) = y         (backward, column layout: lane i owns column i of Lb)
+// so every lane scales by its OWN reciprocal diagonal (computed once, in parallel) and each substitution
+// step on the critical path is one shuffle + one FMA. The transposition goes through padded shared memory
+// (row writes and column reads both conflict-free). Only the lower triangle of L is read.
 // ------------------------------------------------------------------------------------------
-template<typename T, int NP>
-__global__ void __launch_bounds__(256) k_potrs_group(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, size_t strideB,
-                                                      size_t batch) {
-    constexpr int GROUPS = 256 / NP;
-    constexpr int LDP = NP + 1; // padded: row writes and column reads are both conflict-free
+#ifndef GPUB_POTRS_THREADS
+#define GPUB_POTRS_THREADS 128
+#endif
+#ifndef GPUB_POTRS_MINB
+#define GPUB_POTRS_MINB 5
+#endif
+
+template<typename T, int NP, bool DENSE>
+__global__ void __launch_bounds__(GPUB_POTRS_THREADS, GPUB_POTRS_MINB)
+k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b, size_t strideB, size_t batch) {
+    constexpr int GROUPS = GPUB_POTRS_THREADS / NP;
+    constexpr int LDP = NP + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s_t = reinterpret_cast<T *>(smem_raw) + (size_t) (threadIdx.x / NP) * NP * LDP;
     const int grp = threadIdx.x / NP;
     const int i = threadIdx.x % NP;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned gmask = (NP == 32) ? 0xffffffffu : (((1u << NP) - 1u) << (lane & ~(unsigned) (NP - 1)));
+    T *s_t = reinterpret_cast<T *>(smem_raw) + (size_t) grp * NP * LDP;
+    const size_t ldl = DENSE ? (size_t) NP : ldl_rt;
     const size_t ngroups = (size_t) gridDim.x * GROUPS;
-    const bool row_ok = i < n;
+    const size_t iters = (batch + ngroups - 1) / ngroups;
+    const bool row_ok = DENSE || i < n;
 
-    for (size_t mat = (size_t) blockIdx.x * GROUPS + grp; mat < batch; mat += ngroups) {
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * ngroups + (size_t) blockIdx.x * GROUPS + grp;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
         const T *l_g = L + mat * strideL;
         T *b_g = b + mat * strideB;
-        T l[NP];
+        T l[NP]; // strictly lower part of row i
 #pragma unroll
-        for (int c = 0; c < NP; c++) l[c] = (row_ok && c <= i) ? l_g[i + (size_t) c * ldl] : T(c == i ? 1 : 0);
+        for (int c = 0; c < NP; c++) l[c] = (row_ok && c < i) ? l_g[i + (size_t) c * ldl] : T(0);
+        const T diag = row_ok ? l_g[i + (size_t) i * ldl] : T(1);
         T x = row_ok ? b_g[i] : T(0);
-        // reciprocal of the own diagonal entry, all lanes in parallel
-        T dinv = T(1);
+        const T dinv = T(1) / diag;
 #pragma unroll
-        for (int c = 0; c < NP; c++)
-            if (c == i) dinv = T(1) / l[c];
-        // rows -> shared (transposed read below)
-#pragma unroll
-        for (int c = 0; c < NP; c++) s_t[i * LDP + c] = l[c];
-        // forward: L y = b
-#pragma unroll
-        for (int j = 0; j < NP; j++) {
-            if (j < n) {
-                const T yj = __shfl_sync(gmask, x * dinv, j, NP);
-                if (i == j) x = yj;
-                else if (i > j) x = fma(-l[j], yj, x);
-            }
+        for (int c = 0; c < NP; c++) {
+            l[c] *= dinv;
+            s_t[i * LDP + c] = l[c];
         }
-        __syncwarp(gmask);
-        // column layout: lane j holds L(r, j) for r >= j
+        x *= dinv;
+        // forward: Lb y = D^-1 b
+#pragma unroll
+        for (int j = 0; j < NP - 1; j++) {
+            const T yj = __shfl_sync(0xffffffffu, x, j, NP);
+            x = fma(-l[j], yj, x);
+        }
+        __syncwarp();
+        // column i of Lb: Lb(r, i) for r > i, zero elsewhere
 #pragma unroll
         for (int r = 0; r < NP; r++) l[r] = s_t[r * LDP + i];
-        __syncwarp(gmask);
-        // backward: L^T x = y
+        __syncwarp();
+        // backward: Lb^T v = y, z = D^-1 v
 #pragma unroll
-        for (int jj = NP - 1; jj >= 0; jj--) {
-            if (jj < n) {
-                const T xj = __shfl_sync(gmask, x * dinv, jj, NP);
-                if (i == jj) x = xj;
-                else if (i < jj) x = fma(-l[jj], xj, x);
-            }
+        for (int jj = NP - 1; jj > 0; jj--) {
+            const T vj = __shfl_sync(0xffffffffu, x, jj, NP);
+            x = fma(-l[jj], vj, x);
         }
-        if (row_ok) b_g[i] = x;
+        x *= dinv;
+        if (row_ok && live) b_g[i] = x;
     }
 }
 
@@ -241,16 +269,23 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
     GPUB_ENTER(ctx, sidx);
     if (n <= 32) {
         const int np = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
-        const size_t groups = 256 / np;
+        const size_t groups = GPUB_POTRF_THREADS / np;
         const size_t want = gpub_ceil_div(batch, groups);
-        const size_t cap = (size_t) ctx->sm_count * 8;
+        // persistent-style grid: resident CTAs per SM x SM count, every CTA walks the batch with a grid stride
+        const size_t cap = (size_t) ctx->sm_count * GPUB_POTRF_MINB * 2;
         const unsigned grid = (unsigned) (want < cap ? want : cap);
+        constexpr int TH = GPUB_POTRF_THREADS;
+        const bool dense = (n == (size_t) np) && lda == n;
+#define GPUB_POTRF_CASE(NPV)                                                                              \
+    if (dense) k_potrf_group<T, NPV, true><<<grid, TH, 0, stream>>>((int) n, A, lda, strideA, info, batch); \
+    else k_potrf_group<T, NPV, false><<<grid, TH, 0, stream>>>((int) n, A, lda, strideA, info, batch);
         switch (np) {
-            case 4: k_potrf_group<T, 4><<<grid, 256, 0, stream>>>((int) n, A, lda, strideA, info, batch); break;
-            case 8: k_potrf_group<T, 8><<<grid, 256, 0, stream>>>((int) n, A, lda, strideA, info, batch); break;
-            case 16: k_potrf_group<T, 16><<<grid, 256, 0, stream>>>((int) n, A, lda, strideA, info, batch); break;
-            default: k_potrf_group<T, 32><<<grid, 256, 0, stream>>>((int) n, A, lda, strideA, info, batch); break;
+            case 4: GPUB_POTRF_CASE(4) break;
+            case 8: GPUB_POTRF_CASE(8) break;
+            case 16: GPUB_POTRF_CASE(16) break;
+            default: GPUB_POTRF_CASE(32) break;
         }
+#undef GPUB_POTRF_CASE
     } else {
         const size_t bytes = n * n * sizeof(T);
         const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 1024 ? 1 : 0;
@@ -273,23 +308,27 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
     GPUB_ENTER(ctx, sidx);
     if (n <= 32) {
         const int np = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
-        const size_t groups = 256 / np;
+        const size_t groups = GPUB_POTRS_THREADS / np;
         const size_t want = gpub_ceil_div(batch, groups);
-        const size_t cap = (size_t) ctx->sm_count * 8;
+        const size_t cap = (size_t) ctx->sm_count * GPUB_POTRS_MINB * 2;
         const unsigned grid = (unsigned) (want < cap ? want : cap);
         const size_t smem = groups * np * (np + 1) * sizeof(T);
-#define GPUB_POTRS_CASE(NPV)                                                                                         \
+        const bool dense = (n == (size_t) np) && ldl == n;
+#define GPUB_POTRS_LAUNCH(NPV, DN)                                                                                   \
     {                                                                                                                \
-        auto kern = k_potrs_group<T, NPV>;                                                                           \
+        auto kern = k_potrs_group<T, NPV, DN>;                                                                       \
         if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-        kern<<<grid, 256, smem, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);                              \
+        kern<<<grid, GPUB_POTRS_THREADS, smem, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);               \
     }
+#define GPUB_POTRS_CASE(NPV)                                                                                         \
+    if (dense) GPUB_POTRS_LAUNCH(NPV, true) else GPUB_POTRS_LAUNCH(NPV, false)
         switch (np) {
             case 4: GPUB_POTRS_CASE(4) break;
             case 8: GPUB_POTRS_CASE(8) break;
             case 16: GPUB_POTRS_CASE(16) break;
             default: GPUB_POTRS_CASE(32) break;
         }
+#undef GPUB_POTRS_LAUNCH
 #undef GPUB_POTRS_CASE
     } else {
         const size_t smem = n * sizeof(T);
