@@ -18,9 +18,19 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // small matrices: chunk of whole matrices per CTA
 // ------------------------------------------------------------------------------------------
+inline bool ranges_overlap(const void *p, size_t pbytes, const void *q, size_t qbytes) {
+    uintptr_t a = (uintptr_t) p, b = (uintptr_t) q;
+    return a < b + qbytes && b < a + pbytes;
+}
+
 template<typename T> struct Vec16;
 template<> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
 template<> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+
+__device__ __forceinline__ void unpack_v(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack_v(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ double2 pack_v(const double *o) { return make_double2(o[0], o[1]); }
+__device__ __forceinline__ float4 pack_v(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
 
 // cooperative copy of `count` contiguous elements global -> shared (128-bit when both are aligned)
 template<typename T>
@@ -104,6 +114,153 @@ __global__ void __launch_bounds__(256) k_gemm_small(int m, int n, int k, T alpha
         stage_out(C + first * szC, sC, szC * cnt, tid, blockDim.x);
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// square small matrices, N in {4, 8, 16, 32}, dense batch: k_gemm_col<T, N>
+// N lanes per matrix, lane = one column of C (32/N matrices per warp, warps fully independent: no CTA
+// barrier anywhere). Per warp iteration the 32/N matrices are one contiguous 32*N-element chunk of A, B, C:
+//   A : cp.async (16 B per lane, coalesced) into the warp's double-buffered shared slot; the next chunk is
+//       in flight while the current one is multiplied. Each matrix gets 16 B of padding so that the 32/N
+//       different matrices read in one LDS.128 hit different banks; lanes of the same matrix broadcast.
+//   B : the lane's own column, 128-bit loads straight into registers (prefetched one iteration ahead when
+//       the register budget allows);  C : 128-bit stores (plus loads when beta != 0).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_ca(void *smem, const void *gmem) {
+    unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_grp() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int NPEND> __device__ __forceinline__ void cp_async_wait_grp() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+template<typename T, int N>
+struct GemmColCfg {
+    static constexpr int VN = 16 / sizeof(T);                 // elements per 128-bit access
+    static constexpr int MPW = 32 / N;                        // matrices per warp
+    static constexpr int MAT_PAD = N * N + VN;                // padded shared stride of one matrix (elements)
+    static constexpr int SLOT = MPW * MAT_PAD;                // one warp slot (elements)
+    static constexpr int CHUNKS_PER_LANE = (N * (int) sizeof(T)) / 16; // 16-byte pieces of A per lane
+    static constexpr bool PREFETCH_B = (N * sizeof(T) <= 128);
+    static constexpr int WARPS = 4;
+    static constexpr int MINB = (N * sizeof(T) >= 256) ? 2 : ((N * sizeof(T) >= 128) ? 4 : 6);
+};
+
+template<typename T, int N>
+__global__ void __launch_bounds__(GemmColCfg<T, N>::WARPS * 32, GemmColCfg<T, N>::MINB)
+k_gemm_col(T alpha, const T *__restrict__ A, const T *__restrict__ B, T beta, T *C, size_t batch) {
+    using Cfg = GemmColCfg<T, N>;
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Cfg::VN, MPW = Cfg::MPW, NV = N / VN;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T (*s_a)[2][Cfg::SLOT] = reinterpret_cast<T (*)[2][Cfg::SLOT]>(smem_raw); // [warp][buffer][slot]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane / N;
+    const size_t nwarps = (size_t) gridDim.x * Cfg::WARPS;
+    const size_t wg = (size_t) blockIdx.x * Cfg::WARPS + warp;
+    const size_t nchunks = (batch + MPW - 1) / MPW;
+    const size_t iters = (nchunks + nwarps - 1) / nwarps;
+    const size_t total_el = batch * (size_t) (N * N);
+
+    auto issue_a = [&](size_t chunk, int buf) {
+        // the warp's chunk is 32*N contiguous elements; lane l copies 16-byte pieces l, l+32, ...
+        const size_t base = chunk * (size_t) (MPW * N * N);
+#pragma unroll
+        for (int p = 0; p < Cfg::CHUNKS_PER_LANE; p++) {
+            const int piece = lane + 32 * p;                 // 16-byte piece inside the chunk
+            const int el = piece * VN;                       // element offset inside the chunk
+            const int mq = el / (N * N), within = el - mq * (N * N);
+            if (base + el < total_el) cp_async16_ca(&s_a[warp][buf][mq * Cfg::MAT_PAD + within], A + base + el);
+        }
+        cp_async_commit_grp();
+    };
+    auto load_col = [&](const T *src, size_t chunk, T *dst) {
+        const size_t off = chunk * (size_t) (MPW * N * N) + (size_t) lane * N;
+        if (off < total_el) {
+            const V *p = reinterpret_cast<const V *>(src + off);
+#pragma unroll
+            for (int v = 0; v < NV; v++) unpack_v(p[v], dst + v * VN);
+        } else {
+#pragma unroll
+            for (int r = 0; r < N; r++) dst[r] = T(0);
+        }
+    };
+
+    T b_cur[N], b_nxt[Cfg::PREFETCH_B ? N : 1];
+    if (iters > 0) {
+        issue_a(wg, 0);
+        if (Cfg::PREFETCH_B) load_col(B, wg, b_nxt);
+    }
+    for (size_t it = 0; it < iters; it++) {
+        const size_t chunk = it * nwarps + wg;
+        const int buf = (int) (it & 1);
+        if (Cfg::PREFETCH_B) {
+#pragma unroll
+            for (int r = 0; r < N; r++) b_cur[r] = b_nxt[r];
+        } else {
+            load_col(B, chunk, b_cur);
+        }
+        if (it + 1 < iters) {
+            issue_a(chunk + nwarps, buf ^ 1);
+            if (Cfg::PREFETCH_B) load_col(B, chunk + nwarps, b_nxt);
+            cp_async_wait_grp<1>();
+        } else {
+            cp_async_wait_grp<0>();
+        }
+        __syncwarp();
+        const T *a = &s_a[warp][buf][q * Cfg::MAT_PAD];
+        T acc[N];
+#pragma unroll
+        for (int r = 0; r < N; r++) acc[r] = T(0);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            const T bk = b_cur[k];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                T av[VN];
+                unpack_v(*reinterpret_cast<const V *>(a + k * N + v * VN), av);
+#pragma unroll
+                for (int e = 0; e < VN; e++) acc[v * VN + e] = fma(av[e], bk, acc[v * VN + e]);
+            }
+        }
+        __syncwarp(); // every lane is done with slot `buf` before the copy two iterations ahead refills it
+        const size_t off = chunk * (size_t) (MPW * N * N) + (size_t) lane * N;
+        if (off < total_el) {
+            V *cp = reinterpret_cast<V *>(C + off);
+            if (beta == T(0)) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    T o[VN];
+#pragma unroll
+                    for (int e = 0; e < VN; e++) o[e] = alpha * acc[v * VN + e];
+                    cp[v] = pack_v(o);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    T o[VN];
+                    unpack_v(cp[v], o);
+#pragma unroll
+                    for (int e = 0; e < VN; e++) o[e] = alpha * acc[v * VN + e] + beta * o[e];
+                    cp[v] = pack_v(o);
+                }
+            }
+        }
+    }
+}
+
+template<typename T, int N>
+int launch_col(gpub_ctx_t ctx, cudaStream_t stream, T alpha, const T *A, const T *B, T beta, T *C, size_t batch) {
+    using Cfg = GemmColCfg<T, N>;
+    const size_t nchunks = gpub_ceil_div(batch, (size_t) Cfg::MPW);
+    const size_t want = gpub_ceil_div(nchunks, (size_t) Cfg::WARPS);
+    const size_t cap = (size_t) ctx->sm_count * Cfg::MINB * 2;
+    const unsigned grid = (unsigned) (want < cap ? want : cap);
+    const size_t smem = sizeof(T) * Cfg::WARPS * 2 * Cfg::SLOT;
+    if (smem > 48 * 1024)
+        GPUB_CUDA(cudaFuncSetAttribute(k_gemm_col<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    k_gemm_col<T, N><<<grid, Cfg::WARPS * 32, smem, stream>>>(alpha, A, B, beta, C, batch);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,11 +444,6 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
 template<typename T> struct UseDmma { static constexpr bool value = false; };
 template<> struct UseDmma<double> { static constexpr bool value = true; };
 
-inline bool ranges_overlap(const void *p, size_t pbytes, const void *q, size_t qbytes) {
-    uintptr_t a = (uintptr_t) p, b = (uintptr_t) q;
-    return a < b + qbytes && b < a + pbytes;
-}
-
 template<typename T>
 int launch_small(gpub_ctx_t ctx, cudaStream_t stream, int m, int n, int k, T alpha, const T *A, const T *B, T beta, T *C,
                  size_t batch) {
@@ -330,6 +482,18 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
     GPUB_ENTER(ctx, sidx);
 
     const bool dense = lda == m && ldb == k && ldc == m && (batch == 1 || (sA == m * k && sB == k * n && sC == m * n));
+    const bool aligned16 = (((uintptr_t) A | (uintptr_t) B | (uintptr_t) C) & 15u) == 0;
+    const bool no_alias = !ranges_overlap(C, m * n * batch * sizeof(T), A, m * k * batch * sizeof(T)) &&
+                          !ranges_overlap(C, m * n * batch * sizeof(T), B, k * n * batch * sizeof(T));
+    if (dense && aligned16 && no_alias && m == n && n == k && batch >= 2) {
+        switch (m) {
+            case 4: return launch_col<T, 4>(ctx, stream, alpha, A, B, beta, C, batch);
+            case 8: return launch_col<T, 8>(ctx, stream, alpha, A, B, beta, C, batch);
+            case 16: return launch_col<T, 16>(ctx, stream, alpha, A, B, beta, C, batch);
+            case 32: return launch_col<T, 32>(ctx, stream, alpha, A, B, beta, C, batch);
+            default: break;
+        }
+    }
     if (dense && m <= 32 && n <= 32 && k <= 32 && k > 0 && batch >= 2) {
         // every operand of a chunk is staged before C is written, so C may alias A or B chunk-wise
         return launch_small<T>(ctx, stream, (int) m, (int) n, (int) k, alpha, A, B, beta, C, batch);

@@ -7,9 +7,9 @@
 // beta = -sign(alpha) * ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta), and tau = 0
 // (H = I) when x == 0 -- the rule SVD sign parity depends on (hard part 2).
 //
-//   k_gels_warp<T, M, N> : fused gels for small tall systems (cfg3: 64 x 16 fp32). One matrix per warp,
-//        lane l owns rows l, l+32, ... in registers; [A | b] is factored as one M x (N+1) panel, the
-//        column norms and the v^T A products are warp butterflies, R x = Q^T b is solved in registers.
+//   k_gels_sub<T, M, N, LPM> : fused gels for small tall systems (cfg3: 64 x 16 fp32). LPM lanes per matrix,
+//        each lane owns M/LPM consecutive rows of [A | b] in registers (128-bit loads), the column norms and the
+//        v^T A products are log2(LPM)-step butterflies inside the group, R x = Q^T b is solved in registers.
 //   k_geqrf_cta / k_gels_cta / k_ormqr_cta / k_trsv_cta : any shape, one matrix per CTA, staged in shared
 //        memory when it fits, else in place in global memory (L2 resident).
 #include "common.cuh"
@@ -207,85 +207,118 @@ __global__ void __launch_bounds__(QT) k_trsv_cta(int n, const T *__restrict__ R,
 }
 
 // ------------------------------------------------------------------------------------------
-// fused gels for small tall systems, one matrix per warp, everything in registers
-// M rows (multiple of 32), N columns; lane l owns rows l + 32*q
+// fused gels for small tall systems: k_gels_sub<T, M, N, LPM>
+// LPM lanes per matrix (32/LPM matrices per warp), lane l owns the RPL = M/LPM consecutive rows
+// l*RPL .. l*RPL+RPL-1 of [A | b] in registers, so loads/stores are 128-bit and a column of one matrix is one
+// contiguous, fully used run of sectors. Column norms and the v^T a_c products are log2(LPM)-step xor
+// butterflies inside the group (3 steps for LPM = 8 instead of 5 for a full warp, and one shuffle instruction
+// serves all 32/LPM matrices of the warp); the (N-j) products of a column step are independent, so their
+// butterflies pipeline. R x = Q^T b is solved in registers. Control flow is uniform across the CTA.
 // ------------------------------------------------------------------------------------------
-template<typename T, int M, int N>
-__global__ void __launch_bounds__(128) k_gels_warp(T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
-    constexpr int RQ = M / 32; // rows per lane
-    const int lane = threadIdx.x & 31;
-    const size_t warp_global = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
-    for (size_t mat = warp_global; mat < batch; mat += nwarps) {
-        T *a_g = A + mat * sA;
-        T *b_g = b + mat * sB;
-        T a[N + 1][RQ];
+template<typename T> struct VecQ;
+template<> struct VecQ<double> { using type = double2; static constexpr int N = 2; };
+template<> struct VecQ<float> { using type = float4; static constexpr int N = 4; };
+__device__ __forceinline__ void unpack_q(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack_q(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ double2 pack_q(const double *o) { return make_double2(o[0], o[1]); }
+__device__ __forceinline__ float4 pack_q(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+
+template<typename T, int LPM>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int o = LPM / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#ifndef GPUB_GELS_MINB
+#define GPUB_GELS_MINB 2
+#endif
+
+template<typename T, int M, int N, int LPM>
+__global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_sub(T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
+    constexpr int RPL = M / LPM;           // rows per lane
+    constexpr int VN = VecQ<T>::N;
+    constexpr int NV = RPL / VN;           // 128-bit accesses per lane per column
+    using V = typename VecQ<T>::type;
+    static_assert(RPL % VN == 0, "rows per lane must be a multiple of the vector width");
+    constexpr int MPC = 128 / LPM;         // matrices per CTA iteration
+    const int l = threadIdx.x % LPM;       // lane inside the group
+    const int gl = (threadIdx.x & 31) - l; // first lane of the group inside the warp
+    const int row0 = l * RPL;
+    const size_t ngroups = (size_t) gridDim.x * MPC;
+    const size_t iters = (batch + ngroups - 1) / ngroups;
+
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
+        T *a_g = A + mat * sA + row0;
+        T *b_g = b + mat * sB + row0;
+        T a[N + 1][RPL];
 #pragma unroll
         for (int c = 0; c < N; c++)
 #pragma unroll
-            for (int q = 0; q < RQ; q++) a[c][q] = a_g[(size_t) c * M + lane + 32 * q];
+            for (int v = 0; v < NV; v++) unpack_q(reinterpret_cast<const V *>(a_g + (size_t) c * M)[v], &a[c][v * VN]);
 #pragma unroll
-        for (int q = 0; q < RQ; q++) a[N][q] = b_g[lane + 32 * q];
+        for (int v = 0; v < NV; v++) unpack_q(reinterpret_cast<const V *>(b_g)[v], &a[N][v * VN]);
+
         int bad = 0;
-        T rdiag[N]; // R(j,j), replicated in every lane
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            // row j lives in lane (j % 32), slot (j / 32)
-            const int jl = j & 31, jq = j >> 5;
+            // row j lives in lane j / RPL of the group, slot j % RPL (both compile-time)
             T part = 0;
 #pragma unroll
-            for (int q = 0; q < RQ; q++) {
-                const int row = lane + 32 * q;
-                const T v = a[j][q];
-                part = fma(row > j ? v : T(0), v, part);
+            for (int t = 0; t < RPL; t++) {
+                const T x = (row0 + t > j) ? a[j][t] : T(0);
+                part = fma(x, x, part);
             }
-            const T xnorm2 = warp_sum(part);
-            const T alpha = __shfl_sync(0xffffffffu, a[j][jq], jl);
+            const T xnorm2 = group_sum<T, LPM>(part);
+            const T alpha = __shfl_sync(0xffffffffu, a[j][j % RPL], gl + j / RPL);
             T tau, scale;
             const T beta = larfg<T>(alpha, xnorm2, &tau, &scale);
-            rdiag[j] = beta;
             if (beta == T(0) && bad == 0) bad = j + 1;
-            // v = x * scale below the diagonal, 1 on it, 0 above
-            T v[RQ];
+            T v[RPL];
 #pragma unroll
-            for (int q = 0; q < RQ; q++) {
-                const int row = lane + 32 * q;
-                v[q] = row > j ? a[j][q] * scale : (row == j ? T(1) : T(0));
-                if (row > j) a[j][q] = v[q];
-                else if (row == j) a[j][q] = beta;
+            for (int t = 0; t < RPL; t++) {
+                const int row = row0 + t;
+                v[t] = row > j ? a[j][t] * scale : (row == j ? T(1) : T(0));
+                a[j][t] = row > j ? v[t] : (row == j ? beta : a[j][t]);
             }
-            if (tau != T(0)) {
+            T w[N + 1];
 #pragma unroll
-                for (int c = j + 1; c <= N; c++) {
-                    T w = 0;
+            for (int c = j + 1; c <= N; c++) {
+                T acc = 0;
 #pragma unroll
-                    for (int q = 0; q < RQ; q++) w = fma(v[q], a[c][q], w);
-                    w = warp_sum(w);
-                    const T tw = tau * w;
-#pragma unroll
-                    for (int q = 0; q < RQ; q++) a[c][q] = fma(-tw, v[q], a[c][q]);
-                }
+                for (int t = 0; t < RPL; t++) acc = fma(v[t], a[c][t], acc);
+                w[c] = acc;
             }
+#pragma unroll
+            for (int c = j + 1; c <= N; c++) w[c] = tau * group_sum<T, LPM>(w[c]);
+#pragma unroll
+            for (int c = j + 1; c <= N; c++)
+#pragma unroll
+                for (int t = 0; t < RPL; t++) a[c][t] = fma(-w[c], v[t], a[c][t]);
         }
-        // back substitution on R (rows 0..N-1 of the columns; row r in lane r%32, slot r/32)
+        // back substitution on R: row j in lane j / RPL, slot j % RPL
 #pragma unroll
         for (int j = N - 1; j >= 0; j--) {
-            const int jl = j & 31, jq = j >> 5;
-            T xj = __shfl_sync(0xffffffffu, a[N][jq], jl) / rdiag[j];
+            const T xj = __shfl_sync(0xffffffffu, a[N][j % RPL], gl + j / RPL) / __shfl_sync(0xffffffffu, a[j][j % RPL], gl + j / RPL);
 #pragma unroll
-            for (int q = 0; q < RQ; q++) {
-                const int row = lane + 32 * q;
-                if (row == j) a[N][q] = xj;
-                else if (row < j) a[N][q] = fma(-a[j][q], xj, a[N][q]);
+            for (int t = 0; t < RPL; t++) {
+                const int row = row0 + t;
+                if (t < RPL && row0 < N) // only the lanes that hold rows of R
+                    a[N][t] = row == j ? xj : (row < j ? fma(-a[j][t], xj, a[N][t]) : a[N][t]);
             }
         }
+        if (live) {
 #pragma unroll
-        for (int c = 0; c < N; c++)
+            for (int c = 0; c < N; c++)
 #pragma unroll
-            for (int q = 0; q < RQ; q++) a_g[(size_t) c * M + lane + 32 * q] = a[c][q];
+                for (int v = 0; v < NV; v++) reinterpret_cast<V *>(a_g + (size_t) c * M)[v] = pack_q(&a[c][v * VN]);
 #pragma unroll
-        for (int q = 0; q < RQ; q++) b_g[lane + 32 * q] = a[N][q];
-        if (info && lane == 0) info[mat] = bad;
+            for (int v = 0; v < NV; v++) reinterpret_cast<V *>(b_g)[v] = pack_q(&a[N][v * VN]);
+            if (info && l == 0) info[mat] = bad;
+        }
     }
 }
 
@@ -350,15 +383,20 @@ int trsv_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *R, size_t ldr, siz
     return GPUB_OK;
 }
 
-template<typename T, int M, int N>
-int launch_gels_warp(gpub_ctx_t ctx, cudaStream_t stream, T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
-    const size_t want = gpub_ceil_div(batch, 4);
-    const size_t cap = (size_t) ctx->sm_count * 16;
+template<typename T, int M, int N, int LPM>
+int launch_gels_sub(gpub_ctx_t ctx, cudaStream_t stream, T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
+    const size_t want = gpub_ceil_div(batch, (size_t) (128 / LPM));
+    const size_t cap = (size_t) ctx->sm_count * GPUB_GELS_MINB * 2;
     const unsigned grid = (unsigned) (want < cap ? want : cap);
-    k_gels_warp<T, M, N><<<grid, 128, 0, stream>>>(A, sA, b, sB, info, batch);
+    k_gels_sub<T, M, N, LPM><<<grid, 128, 0, stream>>>(A, sA, b, sB, info, batch);
     GPUB_LAUNCH_CHECK();
     return GPUB_OK;
 }
+
+// lanes per matrix: 8 consecutive fp32 rows (or 4 fp64 rows) per lane keeps [A | b] within ~140 registers
+template<typename T> struct GelsLpm;
+template<> struct GelsLpm<float> { static constexpr int rows_per_lane = 8; };
+template<> struct GelsLpm<double> { static constexpr int rows_per_lane = 4; };
 
 template<typename T>
 int gels_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda, size_t sA, T *b, size_t sB, int *info,
@@ -367,10 +405,14 @@ int gels_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda,
     if (!A || !b || lda < m || n > m) return GPUB_EINVAL;
     GPUB_ENTER(ctx, sidx);
     if (n == 0) return GPUB_OK;
-    if (lda == m) {
-        if (m == 64 && n == 16) return launch_gels_warp<T, 64, 16>(ctx, stream, A, sA, b, sB, info, batch);
-        if (m == 32 && n == 16) return launch_gels_warp<T, 32, 16>(ctx, stream, A, sA, b, sB, info, batch);
-        if (m == 32 && n == 8) return launch_gels_warp<T, 32, 8>(ctx, stream, A, sA, b, sB, info, batch);
+    const bool vec_ok = lda == m && ((((uintptr_t) A) | ((uintptr_t) b)) & 15u) == 0 && (sA * sizeof(T)) % 16 == 0 &&
+                        (sB * sizeof(T)) % 16 == 0;
+    if (vec_ok) {
+        constexpr int R = GelsLpm<T>::rows_per_lane;
+        if (m == 64 && n == 16) return launch_gels_sub<T, 64, 16, 64 / R>(ctx, stream, A, sA, b, sB, info, batch);
+        if (m == 32 && n == 16) return launch_gels_sub<T, 32, 16, 32 / R>(ctx, stream, A, sA, b, sB, info, batch);
+        if (m == 32 && n == 8) return launch_gels_sub<T, 32, 8, 32 / R>(ctx, stream, A, sA, b, sB, info, batch);
+        if (m == 16 && n == 8) return launch_gels_sub<T, 16, 8, 16 / R>(ctx, stream, A, sA, b, sB, info, batch);
     }
     const size_t bytes = qr_smem_bytes<T>(m, n, true);
     if (bytes > (size_t) ctx->max_smem_optin - 2048) {
