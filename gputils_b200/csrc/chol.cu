@@ -99,6 +99,99 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 }
 
 // ------------------------------------------------------------------------------------------
+// potrf, 32 < n <= 32*NB (NB = 2, 3, 4): k_potrf_blk<T, NB>, one matrix per CTA.
+// The matrix is cut into 32 x 32 blocks; one warp owns one block of the lower triangle for the whole
+// factorisation (lane = row of the block, the 32 entries of that row in registers). Blocked right-looking:
+//   for each block column hb:
+//     (1) the diagonal warp factorises its block exactly like k_potrf_group (shuffled pivot, rsqrt, column
+//         broadcast through shared memory) and leaves L11 and the reciprocal pivots in shared memory;
+//     (2) the warps below solve L21 = A21 L11^-T with no inter-lane dependency at all (every lane owns a row)
+//         and leave their block in shared memory, stored [k][row];
+//     (3) every trailing warp applies its rank-32 update a(row, c) -= sum_k L(row, k) L(c, k): its own row
+//         comes from the panel block of its block row (conflict-free), the other factor is a 128-bit
+//         broadcast from the panel block of its block column.
+// Three CTA barriers per block column instead of two per column. Rows / columns beyond n are an identity pad.
+// ------------------------------------------------------------------------------------------
+// resident CTAs per SM the register allocation is tuned for
+template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : (sizeof(T) == 8 ? 1 : 2)); };
+
+template<typename T, int NB>
+__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_blk(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
+    constexpr int NW = NB * (NB + 1) / 2;
+    __shared__ __align__(16) T s_p[NB][32][32]; // panel blocks of the current block column: [block row][k][row]
+    __shared__ T s_rinv[32];
+    __shared__ int s_bad;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // enumerate the lower-triangular blocks: warp -> (rb, h), rb >= h
+    int rb = 0;
+    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
+    const int h = warp - rb * (rb + 1) / 2;
+    const int row = 32 * rb + lane;
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *a_g = A + mat * strideA;
+        T a[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int col = 32 * h + c;
+            a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
+        }
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int hb = 0; hb < NB; hb++) {
+            if (rb == hb && h == hb) { // (1) diagonal block
+                int bad = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const T d = __shfl_sync(0xffffffffu, a[j], j);
+                    if (!(d > T(0)) && bad == 0) bad = j + 1;
+                    const T r = fast_rsqrt<T>(d);
+                    const T l = a[j] * r;
+                    a[j] = l;
+                    s_p[hb][j][lane] = l;
+                    if (lane == j) s_rinv[j] = r;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[hb][j][c], a[c]);
+                }
+                if (lane == 0 && bad != 0 && s_bad == 0) s_bad = 32 * hb + bad;
+            }
+            __syncthreads();
+            if (h == hb && rb > hb) { // (2) panel blocks: rows below the diagonal block
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const T l = a[j] * s_rinv[j];
+                    a[j] = l;
+                    s_p[rb][j][lane] = l;
+#pragma unroll
+                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[hb][j][c], a[c]);
+                }
+            }
+            __syncthreads();
+            if (h > hb) { // (3) trailing blocks (rb >= h > hb)
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const T lk = s_p[rb][k][lane];
+#pragma unroll
+                    for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[h][k][c], a[c]);
+                }
+            }
+            __syncthreads();
+        }
+        if (row < n) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int col = 32 * h + c;
+                if (col <= row) a_g[row + (size_t) col * lda] = a[c];
+            }
+        }
+        if (threadIdx.x == 0) info[mat] = s_bad;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // potrf, any n: one CTA per matrix (shared memory when it fits, else in place in global memory)
 // ------------------------------------------------------------------------------------------
 template<typename T>
@@ -286,6 +379,12 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
             default: GPUB_POTRF_CASE(32) break;
         }
 #undef GPUB_POTRF_CASE
+    } else if (n <= 128) {
+        const size_t cap = (size_t) ctx->sm_count * 8;
+        const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+        if (n <= 64) k_potrf_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+        else if (n <= 96) k_potrf_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+        else k_potrf_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, A, lda, strideA, info, batch);
     } else {
         const size_t bytes = n * n * sizeof(T);
         const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 1024 ? 1 : 0;

@@ -441,6 +441,202 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 register-tiled kernel (plain FFMA, no TF32): k_sgemm_rt<BM, BN, TM, TN>
+// CTA tile BM x BN, thread tile TM x TN, K panels of 16 double-buffered with cp.async. A panels land as
+// As[k][row] (row-contiguous, read with 128-bit loads), B panels as Bs[col][k] (k-contiguous, one 128-bit
+// load gives 4 consecutive k for one column), so 4 k-steps cost TM/4*4 + TN LDS.128 for 4*TM*TN FFMA.
+// Requires m % BM == 0, n % BN == 0, k % 16 == 0 and 16-byte aligned operands (the launcher checks).
+// ------------------------------------------------------------------------------------------
+template<int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm_rt(size_t m, size_t n, size_t k, float alpha, const float *__restrict__ A,
+                                                                    size_t lda, size_t sA, const float *__restrict__ B, size_t ldb, size_t sB,
+                                                                    float beta, float *C, size_t ldc, size_t sC, size_t tiles_m, size_t tiles_n,
+                                                                    size_t batch) {
+    constexpr int BK = 16;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int TX = BM / TM; // threads along rows
+    constexpr int LDB_S = BK + 4; // padded k-stride of the B panel (keeps 16-byte alignment, spreads banks)
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Bs[2][BN][LDB_S];
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const size_t tiles = tiles_m * tiles_n;
+    for (size_t t = blockIdx.x; t < tiles * batch; t += gridDim.x) {
+        const size_t b = t / tiles, r = t - b * tiles;
+        const size_t row0 = (r % tiles_m) * BM, col0 = (r / tiles_m) * BN;
+        const float *a = A + b * sA + row0;
+        const float *bb = B + b * sB + col0 * ldb;
+        float acc[TN][TM];
+#pragma unroll
+        for (int j = 0; j < TN; j++)
+#pragma unroll
+            for (int i = 0; i < TM; i++) acc[j][i] = 0.f;
+
+        auto load_panel = [&](int buf, size_t k0) {
+            // A: BK columns of BM rows -> BK*BM/4 16-byte pieces
+            for (int e = tid; e < BK * BM / 4; e += NT) {
+                const int rr = (e % (BM / 4)) * 4, kk = e / (BM / 4);
+                cp_async16(&As[buf][kk][rr], a + rr + (k0 + kk) * lda);
+            }
+            // B: BN columns of BK k -> BN*BK/4 pieces
+            for (int e = tid; e < BN * BK / 4; e += NT) {
+                const int kk = (e % (BK / 4)) * 4, cc = e / (BK / 4);
+                cp_async16(&Bs[buf][cc][kk], bb + (k0 + kk) + (size_t) cc * ldb);
+            }
+            cp_async_commit();
+        };
+
+        const size_t npan = k / BK;
+        load_panel(0, 0);
+        for (size_t p = 0; p < npan; p++) {
+            const int buf = (int) (p & 1);
+            if (p + 1 < npan) {
+                load_panel(buf ^ 1, (p + 1) * BK);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k4 = 0; k4 < BK; k4 += 4) {
+                float bv[TN][4];
+#pragma unroll
+                for (int j = 0; j < TN; j++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][ty * TN + j][k4]);
+                    bv[j][0] = v.x; bv[j][1] = v.y; bv[j][2] = v.z; bv[j][3] = v.w;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    float av[TM];
+#pragma unroll
+                    for (int i = 0; i < TM; i += 4) {
+                        // rows of a thread are TM/4 groups of 4, the groups BM/(TM/4) apart: consecutive threads read
+                        // consecutive 16-byte pieces (conflict-free)
+                        const float4 v = *reinterpret_cast<const float4 *>(&As[buf][k4 + kk][(i / 4) * (BM / (TM / 4)) + tx * 4]);
+                        av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < TN; j++)
+#pragma unroll
+                        for (int i = 0; i < TM; i++) acc[j][i] = fmaf(av[i], bv[j][kk], acc[j][i]);
+                }
+            }
+            __syncthreads();
+        }
+        float *c = C + b * sC + row0 + tx * 4 + (col0 + ty * TN) * ldc;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                float4 *p = reinterpret_cast<float4 *>(c + (i / 4) * (BM / (TM / 4)) + (size_t) j * ldc);
+                float4 o;
+                if (beta == 0.f) {
+                    o = make_float4(alpha * acc[j][i], alpha * acc[j][i + 1], alpha * acc[j][i + 2], alpha * acc[j][i + 3]);
+                } else {
+                    const float4 old = *p;
+                    o = make_float4(alpha * acc[j][i] + beta * old.x, alpha * acc[j][i + 1] + beta * old.y,
+                                    alpha * acc[j][i + 2] + beta * old.z, alpha * acc[j][i + 3] + beta * old.w);
+                }
+                *p = o;
+            }
+        }
+    }
+}
+
+template<typename T>
+bool try_sgemm_rt(gpub_ctx_t, cudaStream_t, size_t, size_t, size_t, T, const T *, size_t, size_t, const T *, size_t, size_t, T, T *,
+                  size_t, size_t, size_t) { return false; }
+
+template<>
+bool try_sgemm_rt<float>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n, size_t k, float alpha, const float *A, size_t lda,
+                         size_t sA, const float *B, size_t ldb, size_t sB, float beta, float *C, size_t ldc, size_t sC, size_t batch) {
+    const bool al = ((((uintptr_t) A) | ((uintptr_t) B) | ((uintptr_t) C)) % 16 == 0) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
+                    sA % 4 == 0 && sB % 4 == 0 && sC % 4 == 0;
+    if (!al || k % 16 != 0 || k < 16) return false;
+    const size_t cap = (size_t) ctx->sm_count * 8;
+    if (m % 128 == 0 && n % 128 == 0) {
+        const size_t tm = m / 128, tn = n / 128, total = tm * tn * batch;
+        k_sgemm_rt<128, 128, 8, 8><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+        return true;
+    }
+    if (m % 64 == 0 && n % 64 == 0) {
+        const size_t tm = m / 64, tn = n / 64, total = tm * tn * batch;
+        k_sgemm_rt<64, 64, 4, 8><<<(unsigned) (total < cap ? total : cap), 128, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp64, N = 16 or 32, dense batch: k_dgemm_frag<N> -- one warp per matrix, FP64 tensor-core tiles fed
+// straight from global memory. The m8n8k4 operand fragments map onto column-major storage so that every
+// LDG.64 of a warp reads whole 32-byte sectors (A fragment: 8 consecutive rows x 4 columns, B fragment:
+// 4 consecutive k x 8 columns); nothing is staged in shared memory and there is no barrier. The k loop is
+// fully unrolled so the loads of later k-steps are in flight while earlier DMMAs issue.
+// ------------------------------------------------------------------------------------------
+template<int N>
+__global__ void __launch_bounds__(128, N == 32 ? 3 : 6) k_dgemm_frag(double alpha, const double *__restrict__ A, const double *__restrict__ B,
+                                                                     double beta, double *C, size_t batch) {
+    constexpr int NT = N / 8, KS = N / 4;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const size_t nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    const size_t wg = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t iters = (batch + nwarps - 1) / nwarps;
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * nwarps + wg;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
+        const double *a = A + mat * (size_t) (N * N) + g + (size_t) q * N;       // A(8i + g, 4ks + q)
+        const double *b = B + mat * (size_t) (N * N) + q + (size_t) g * N;       // B(4ks + q, 8j + g)
+        double acc[NT][NT][2];
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            double af[NT], bf[NT];
+#pragma unroll
+            for (int i = 0; i < NT; i++) af[i] = a[8 * i + (size_t) (4 * ks) * N];
+#pragma unroll
+            for (int j = 0; j < NT; j++) bf[j] = b[4 * ks + (size_t) (8 * j) * N];
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (live) {
+            double *c = C + mat * (size_t) (N * N) + g + (size_t) (2 * q) * N;  // C(8i + g, 8j + 2q + e)
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        double *p = c + 8 * i + (size_t) (8 * j + e) * N;
+                        *p = (beta == 0.0) ? alpha * acc[i][j][e] : alpha * acc[i][j][e] + beta * (*p);
+                    }
+        }
+    }
+}
+
+template<typename T, int N>
+bool try_dgemm_frag(gpub_ctx_t, cudaStream_t, T, const T *, const T *, T, T *, size_t) { return false; }
+template<>
+bool try_dgemm_frag<double, 16>(gpub_ctx_t ctx, cudaStream_t stream, double alpha, const double *A, const double *B, double beta, double *C, size_t batch) {
+    const size_t want = gpub_ceil_div(batch, 4), cap = (size_t) ctx->sm_count * 12;
+    k_dgemm_frag<16><<<(unsigned) (want < cap ? want : cap), 128, 0, stream>>>(alpha, A, B, beta, C, batch);
+    return true;
+}
+template<>
+bool try_dgemm_frag<double, 32>(gpub_ctx_t ctx, cudaStream_t stream, double alpha, const double *A, const double *B, double beta, double *C, size_t batch) {
+    const size_t want = gpub_ceil_div(batch, 4), cap = (size_t) ctx->sm_count * 6;
+    k_dgemm_frag<32><<<(unsigned) (want < cap ? want : cap), 128, 0, stream>>>(alpha, A, B, beta, C, batch);
+    return true;
+}
+
 template<typename T> struct UseDmma { static constexpr bool value = false; };
 template<> struct UseDmma<double> { static constexpr bool value = true; };
 
@@ -489,8 +685,12 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
         switch (m) {
             case 4: return launch_col<T, 4>(ctx, stream, alpha, A, B, beta, C, batch);
             case 8: return launch_col<T, 8>(ctx, stream, alpha, A, B, beta, C, batch);
-            case 16: return launch_col<T, 16>(ctx, stream, alpha, A, B, beta, C, batch);
-            case 32: return launch_col<T, 32>(ctx, stream, alpha, A, B, beta, C, batch);
+            case 16:
+                if (try_dgemm_frag<T, 16>(ctx, stream, alpha, A, B, beta, C, batch)) { GPUB_LAUNCH_CHECK(); return GPUB_OK; }
+                return launch_col<T, 16>(ctx, stream, alpha, A, B, beta, C, batch);
+            case 32:
+                if (try_dgemm_frag<T, 32>(ctx, stream, alpha, A, B, beta, C, batch)) { GPUB_LAUNCH_CHECK(); return GPUB_OK; }
+                return launch_col<T, 32>(ctx, stream, alpha, A, B, beta, C, batch);
             default: break;
         }
     }
@@ -529,6 +729,7 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
             done = true;
         }
     }
+    if (!done) done = try_sgemm_rt<T>(ctx, stream, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     if (!done)
         k_gemm_tiled<T><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
     GPUB_LAUNCH_CHECK();

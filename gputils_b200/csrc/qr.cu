@@ -158,6 +158,205 @@ __global__ void __launch_bounds__(QT) k_qr_cta(int m, int n, T *A, size_t lda, s
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Blocked Householder QR for tall matrices that do not fit in shared memory (cfg4: 1024 x 128 fp64):
+// k_geqrf_wy<T, NBQ>, one matrix per CTA, compact-WY with panels of NBQ columns.
+//   panel   : the m x NBQ panel lives in shared memory, stored [column][row] (conflict-free for lanes walking
+//             rows). Per column: (A) |x|^2, (B) larfg by one thread, (C) scale v and, in the same sweep, the
+//             dot products of v with the remaining panel columns and with the previous reflectors (those give
+//             the column of the triangular factor T), (D) rank-1 update of the remaining panel columns fused
+//             with the |x|^2 accumulation of the next column: 3 CTA barriers per column.
+//   trailing: A2 <- (I - V T^T V^T) A2. Each warp takes two trailing columns at a time: one sweep over the
+//             rows accumulates V^T a for both columns (NBQ shared loads feed 2*NBQ FMAs), a butterfly reduces
+//             them, every lane forms W = T^T (V^T a) redundantly, a second sweep applies a -= V W.
+//             V is made explicit in shared memory (unit diagonal, zeros above) so the sweeps are branch-free.
+// The matrix itself stays in global memory (1 MB per matrix: L2 resident while its CTA works on it).
+// ------------------------------------------------------------------------------------------
+template<typename T, int NBQ>
+__global__ void __launch_bounds__(QT) k_geqrf_wy(int m, int n, T *A, size_t lda, size_t sA, T *tau, size_t sTau, size_t batch, int ldv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Vp = reinterpret_cast<T *>(smem_raw);          // [NBQ][ldv]
+    T *Tm = Vp + (size_t) NBQ * ldv;                  // [NBQ][NBQ], T(i, k) at Tm[i * NBQ + k], upper triangular
+    T *s_red = Tm + NBQ * NBQ;                        // [QT/32][NBQ] per-warp partial sums
+    T *s_misc = s_red + (QT / 32) * NBQ;              // tau, scale, ...
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARP = QT / 32;
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *a_g = A + mat * sA;
+        T *tau_g = tau + mat * sTau;
+        const int kmax = n < m ? n : m;
+        for (int j0 = 0; j0 < kmax; j0 += NBQ) {
+            const int nb = (kmax - j0) < NBQ ? (kmax - j0) : NBQ;
+            const int rows = m - j0;
+            // ---- load the panel: rows j0.., columns j0..j0+nb-1 ----
+            for (int k = 0; k < nb; k++)
+                for (int r = tid; r < rows; r += QT) Vp[(size_t) k * ldv + r] = a_g[(size_t) (j0 + r) + (size_t) (j0 + k) * lda];
+            for (int e = tid; e < NBQ * NBQ; e += QT) Tm[e] = T(0);
+            __syncthreads();
+            // |x|^2 of column 0 (rows > 0)
+            T nrm_part = 0;
+            for (int r = 1 + tid; r < rows; r += QT) nrm_part = fma(Vp[r], Vp[r], nrm_part);
+            for (int jj = 0; jj < nb; jj++) {
+                T *vj = Vp + (size_t) jj * ldv;
+                // (A) finish the norm
+                nrm_part = warp_sum(nrm_part);
+                if (lane == 0) s_red[warp * NBQ] = nrm_part;
+                __syncthreads();
+                // (B) reflector parameters
+                if (tid == 0) {
+                    T x2 = 0;
+                    for (int w = 0; w < NWARP; w++) x2 += s_red[w * NBQ];
+                    T t, sc;
+                    const T beta = larfg<T>(vj[jj], x2, &t, &sc);
+                    vj[jj] = beta;
+                    s_misc[0] = t;
+                    s_misc[1] = sc;
+                    tau_g[j0 + jj] = t;
+                    Tm[jj * NBQ + jj] = t;
+                }
+                __syncthreads();
+                const T tj = s_misc[0], scale = s_misc[1];
+                // (C) scale v; dots with the remaining panel columns (slots jj+1..nb-1) and previous reflectors (slots 0..jj-1)
+                T dots[NBQ];
+#pragma unroll
+                for (int c = 0; c < NBQ; c++) dots[c] = T(0);
+                if (tj != T(0)) {
+                    for (int r = jj + tid; r < rows; r += QT) {
+                        T v = T(1);
+                        if (r > jj) {
+                            v = vj[r] * scale;
+                            vj[r] = v;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NBQ; c++) {
+                            if (c < nb && c != jj) {
+                                // previous reflector i = c < jj: its entry at row r (r >= jj > i) is stored; unit / zero parts never reached
+                                dots[c] = fma(v, Vp[(size_t) c * ldv + r], dots[c]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NBQ; c++) {
+                    const T d = warp_sum(dots[c]);
+                    if (lane == 0) s_red[warp * NBQ + c] = d;
+                }
+                __syncthreads();
+                // (D) update the remaining panel columns, column jj of T, and start the next norm
+#pragma unroll
+                for (int c = 0; c < NBQ; c++) {
+                    T d = 0;
+#pragma unroll
+                    for (int w = 0; w < NWARP; w++) d += s_red[w * NBQ + c];
+                    dots[c] = d;
+                }
+                nrm_part = 0;
+                if (tj != T(0)) {
+                    for (int r = jj + tid; r < rows; r += QT) {
+                        const T v = r > jj ? vj[r] : T(1);
+#pragma unroll
+                        for (int c = 0; c < NBQ; c++) {
+                            if (c > jj && c < nb) {
+                                T *pc = Vp + (size_t) c * ldv + r;
+                                const T nv = fma(-tj * dots[c], v, *pc);
+                                *pc = nv;
+                                if (c == jj + 1 && r > jj + 1) nrm_part = fma(nv, nv, nrm_part);
+                            }
+                        }
+                    }
+                } else if (jj + 1 < nb) {
+                    for (int r = jj + 2 + tid; r < rows; r += QT) {
+                        const T x = Vp[(size_t) (jj + 1) * ldv + r];
+                        nrm_part = fma(x, x, nrm_part);
+                    }
+                }
+                if (warp == 0 && jj > 0) {
+                    // T(0:jj, jj) = -tau_j * T(0:jj, 0:jj) * (V(:, 0:jj)^T v_j); lane i computes row i
+                    if (lane < NBQ) {
+                        T d = 0;
+                        for (int w = 0; w < NWARP; w++) d += s_red[w * NBQ + lane];
+                        s_misc[2 + lane] = d;
+                    }
+                    __syncwarp();
+                    if (lane < jj) {
+                        T acc = 0;
+                        for (int i2 = lane; i2 < jj; i2++) acc = fma(Tm[lane * NBQ + i2], s_misc[2 + i2], acc);
+                        Tm[lane * NBQ + jj] = -tj * acc;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- write the factored panel back (R above / on the diagonal, reflectors below) ----
+            for (int k = 0; k < nb; k++)
+                for (int r = tid; r < rows; r += QT) a_g[(size_t) (j0 + r) + (size_t) (j0 + k) * lda] = Vp[(size_t) k * ldv + r];
+            __syncthreads();
+            const int ntrail = n - (j0 + nb);
+            if (ntrail > 0) {
+                // explicit V: zeros above, ones on the diagonal
+                for (int e = tid; e < nb * nb; e += QT) {
+                    const int k = e / nb, r = e % nb;
+                    if (r <= k) Vp[(size_t) k * ldv + r] = (r == k) ? T(1) : T(0);
+                }
+                __syncthreads();
+                for (int cp = warp * 2; cp < ntrail; cp += NWARP * 2) {
+                    const bool two = cp + 1 < ntrail;
+                    T *c0 = a_g + (size_t) j0 + (size_t) (j0 + nb + cp) * lda;
+                    T *c1 = two ? c0 + lda : c0;
+                    T w0[NBQ], w1[NBQ];
+#pragma unroll
+                    for (int k = 0; k < NBQ; k++) w0[k] = w1[k] = T(0);
+#pragma unroll 4
+                    for (int r = lane; r < rows; r += 32) {
+                        const T x0 = c0[r], x1 = c1[r];
+#pragma unroll
+                        for (int k = 0; k < NBQ; k++) {
+                            if (k < nb) {
+                                const T v = Vp[(size_t) k * ldv + r];
+                                w0[k] = fma(v, x0, w0[k]);
+                                w1[k] = fma(v, x1, w1[k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NBQ; k++) {
+                        w0[k] = warp_sum(w0[k]);
+                        w1[k] = warp_sum(w1[k]);
+                    }
+                    // W = T^T w  (W_k = sum_{i <= k} T(i, k) w_i), computed downwards in place from the last entry
+#pragma unroll
+                    for (int k = NBQ - 1; k >= 0; k--) {
+                        T s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int i2 = 0; i2 <= k; i2++) {
+                            const T t = Tm[i2 * NBQ + k];
+                            s0 = fma(t, w0[i2], s0);
+                            s1 = fma(t, w1[i2], s1);
+                        }
+                        w0[k] = s0;
+                        w1[k] = s1;
+                    }
+#pragma unroll 4
+                    for (int r = lane; r < rows; r += 32) {
+                        T x0 = c0[r], x1 = c1[r];
+#pragma unroll
+                        for (int k = 0; k < NBQ; k++) {
+                            if (k < nb) {
+                                const T v = Vp[(size_t) k * ldv + r];
+                                x0 = fma(-v, w0[k], x0);
+                                x1 = fma(-v, w1[k], x1);
+                            }
+                        }
+                        c0[r] = x0;
+                        if (two) c1[r] = x1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // C <- Q^T C (trans) or Q C: every warp owns whole columns of C, so no CTA-wide synchronisation
 template<typename T>
 __global__ void __launch_bounds__(QT) k_ormqr_cta(int trans, int m, int ncols, int k, const T *__restrict__ A, size_t lda, size_t sA,
@@ -335,6 +534,27 @@ int geqrf_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda
     GPUB_ENTER(ctx, sidx);
     const size_t bytes = qr_smem_bytes<T>(m, n, false);
     const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 2048 ? 1 : 0;
+    if (!use_smem || (m >= 256 && n >= 32)) {
+        // blocked compact-WY: the widest panel whose [NBQ][m] block fits in shared memory
+        const size_t ldv = (m + 3) / 4 * 4 + 4;
+        const size_t avail = (size_t) ctx->max_smem_optin - 4096;
+        auto need = [&](size_t nbq) { return (nbq * ldv + nbq * nbq + (QT / 32) * nbq + 8 + nbq) * sizeof(T); };
+        const size_t cap = (size_t) ctx->sm_count * 2;
+        const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+#define GPUB_WY_LAUNCH(NBQV)                                                                                        \
+    {                                                                                                                \
+        const size_t smem = need(NBQV);                                                                              \
+        if (smem > 48 * 1024)                                                                                        \
+            GPUB_CUDA(cudaFuncSetAttribute(k_geqrf_wy<T, NBQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        k_geqrf_wy<T, NBQV><<<grid, QT, smem, stream>>>((int) m, (int) n, A, lda, sA, tau, sTau, batch, (int) ldv);  \
+        GPUB_LAUNCH_CHECK();                                                                                         \
+        return GPUB_OK;                                                                                              \
+    }
+        if (need(16) <= avail && n >= 16) GPUB_WY_LAUNCH(16)
+        if (need(8) <= avail) GPUB_WY_LAUNCH(8)
+        if (need(4) <= avail) GPUB_WY_LAUNCH(4)
+#undef GPUB_WY_LAUNCH
+    }
     const size_t smem = use_smem ? bytes : 0;
     if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(k_qr_cta<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const size_t cap = (size_t) ctx->sm_count * 4;

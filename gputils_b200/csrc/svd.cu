@@ -60,6 +60,215 @@ __global__ void k_init_u(int m, int n, const T *__restrict__ Ur, size_t sUr, T *
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// One-sided Jacobi SVD of R (n x n upper triangular, the geqrf output), one CTA per matrix.
+// Works on X = R^T (lower triangular: the better-conditioned choice after a QR step) held in shared memory,
+// column p of X = row p of R. Right rotations orthogonalise the columns: X J = W D, so
+//     R = J D W^T  =>  singular values D, Vt rows = normalised columns of X J, Ur = J (accumulated only when
+// U is wanted; J lives in global/L2 memory). Pairs follow the round-robin (circle) ordering: n/2 disjoint
+// pairs per round, one warp per pair, a CTA barrier per round, sweeps until no pair rotates.
+// Columns with a negligible norm (rank deficiency) are replaced by an orthonormal completion so Vt is always
+// an orthogonal matrix, which Nullspace relies on.
+// ------------------------------------------------------------------------------------------
+constexpr int JT = 512; // threads per CTA
+
+template<typename T> struct JacobiEps;
+template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; };
+template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; };
+
+template<typename T>
+__device__ __forceinline__ T jwarp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template<typename T>
+__global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A, size_t lda, size_t sA, T *S, size_t sS, T *Vt, size_t ldvt,
+                                                  size_t sVt, T *Ur, size_t sUr, int want_u, int *info, size_t batch, int ldx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *X = reinterpret_cast<T *>(smem_raw);            // [n][ldx]
+    T *s_sig = X + (size_t) n * ldx;                    // [n] column norms
+    T *s_coef = s_sig + n;                              // [n] projection coefficients (completion)
+    int *s_perm = reinterpret_cast<int *>(s_coef + n);  // [n] sorted position -> column
+    __shared__ int s_rot;
+    __shared__ T s_val[JT / 32];
+    __shared__ int s_idx[JT / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = JT / 32;
+    const int npad = n + (n & 1);                       // circle method needs an even count; index n is a bye
+    const T tol = (T) JacobiEps<T>::v * sqrt((T) n);
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        const T *a_g = A + mat * sA;
+        T *J = want_u ? Ur + mat * sUr : nullptr;
+        for (int e = tid; e < n * n; e += JT) {
+            const int p = e / n, r = e % n;              // X(r, p) = R(p, r)
+            X[(size_t) p * ldx + r] = (p <= r) ? a_g[p + (size_t) r * lda] : T(0);
+            if (want_u) J[e] = (p == r) ? T(1) : T(0);   // J(r, p) at J[r + p*n]; identity is symmetric
+        }
+        __syncthreads();
+        int sweep = 0;
+        for (; sweep < 40; sweep++) {
+            if (tid == 0) s_rot = 0;
+            __syncthreads();
+            for (int round = 0; round < npad - 1; round++) {
+                for (int i = warp; i < npad / 2; i += NW) {
+                    int p, q;
+                    if (i == 0) {
+                        p = npad - 1;
+                        q = round;
+                    } else {
+                        p = (round + i) % (npad - 1);
+                        q = (round - i + (npad - 1)) % (npad - 1);
+                    }
+                    if (p >= n || q >= n) continue;      // bye
+                    if (p > q) { int t = p; p = q; q = t; }
+                    T *xp = X + (size_t) p * ldx, *xq = X + (size_t) q * ldx;
+                    T aa = 0, bb = 0, cc = 0;
+                    for (int r = lane; r < n; r += 32) {
+                        const T u = xp[r], v = xq[r];
+                        aa = fma(u, u, aa);
+                        bb = fma(v, v, bb);
+                        cc = fma(u, v, cc);
+                    }
+                    aa = jwarp_sum(aa); bb = jwarp_sum(bb); cc = jwarp_sum(cc);
+                    if (fabs(cc) > tol * sqrt(aa * bb) && cc != T(0)) {
+                        const T zeta = (bb - aa) / (T(2) * cc);
+                        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+                        const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
+                        for (int r = lane; r < n; r += 32) {
+                            const T u = xp[r], v = xq[r];
+                            xp[r] = cs * u - sn * v;
+                            xq[r] = sn * u + cs * v;
+                        }
+                        if (want_u) {
+                            T *jp = J + (size_t) p * n, *jq = J + (size_t) q * n;
+                            for (int r = lane; r < n; r += 32) {
+                                const T u = jp[r], v = jq[r];
+                                jp[r] = cs * u - sn * v;
+                                jq[r] = sn * u + cs * v;
+                            }
+                        }
+                        if (lane == 0) s_rot = 1;
+                    }
+                }
+                __syncthreads();
+            }
+            if (s_rot == 0) break;
+            __syncthreads();
+        }
+        // column norms
+        for (int p = warp; p < n; p += NW) {
+            T aa = 0;
+            for (int r = lane; r < n; r += 32) aa = fma(X[(size_t) p * ldx + r], X[(size_t) p * ldx + r], aa);
+            aa = jwarp_sum(aa);
+            if (lane == 0) s_sig[p] = sqrt(aa);
+        }
+        __syncthreads();
+        // rank sort, descending (ties broken by column index)
+        for (int p = tid; p < n; p += JT) {
+            const T sp = s_sig[p];
+            int rank = 0;
+            for (int q = 0; q < n; q++) {
+                const T sq = s_sig[q];
+                rank += (sq > sp || (sq == sp && q < p)) ? 1 : 0;
+            }
+            s_perm[rank] = p;
+        }
+        __syncthreads();
+        T *s_g = S + mat * sS;
+        for (int i = tid; i < n; i += JT) s_g[i] = s_sig[s_perm[i]];
+        const T smax = s_sig[s_perm[0]];
+        const T thr = smax * (T) n * (T) JacobiEps<T>::v;
+        // normalise the columns that carry a singular value; count them
+        int nfull = 0;
+        for (int i = 0; i < n; i++) nfull += (s_sig[s_perm[i]] > thr) ? 1 : 0;   // sorted: the first nfull positions
+        for (int i = warp; i < nfull; i += NW) {
+            T *xp = X + (size_t) s_perm[i] * ldx;
+            const T inv = T(1) / s_sig[s_perm[i]];
+            for (int r = lane; r < n; r += 32) xp[r] *= inv;
+        }
+        __syncthreads();
+        // orthonormal completion of the null columns, one at a time
+        for (int i = nfull; i < n; i++) {
+            T *xz = X + (size_t) s_perm[i] * ldx;
+            // pick the unit vector e_k with the largest component outside span(final columns): 1 - sum_w w[k]^2
+            T best = T(-1);
+            int bestk = 0;
+            for (int k = tid; k < n; k += JT) {
+                T acc = T(1);
+                for (int w = 0; w < i; w++) {
+                    const T x = X[(size_t) s_perm[w] * ldx + k];
+                    acc = fma(-x, x, acc);
+                }
+                if (acc > best) { best = acc; bestk = k; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+                if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+            }
+            if (lane == 0) { s_val[warp] = best; s_idx[warp] = bestk; }
+            __syncthreads();
+            best = s_val[0]; bestk = s_idx[0];
+            for (int w = 1; w < NW; w++)
+                if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bestk)) { best = s_val[w]; bestk = s_idx[w]; }
+            __syncthreads();
+            for (int r = tid; r < n; r += JT) xz[r] = (r == bestk) ? T(1) : T(0);
+            __syncthreads();
+            for (int pass = 0; pass < 2; pass++) {     // project out the final columns, twice
+                // coefficients g_w = w . z, one final column per warp iteration
+                for (int w = warp; w < i; w += NW) {
+                    const T *xw = X + (size_t) s_perm[w] * ldx;
+                    T g = 0;
+                    for (int r = lane; r < n; r += 32) g = fma(xw[r], xz[r], g);
+                    g = jwarp_sum(g);
+                    if (lane == 0) s_coef[w] = g;
+                }
+                __syncthreads();
+                for (int r = tid; r < n; r += JT) {
+                    T acc = xz[r];
+                    for (int w = 0; w < i; w++) acc = fma(-s_coef[w], X[(size_t) s_perm[w] * ldx + r], acc);
+                    xz[r] = acc;
+                }
+                __syncthreads();
+            }
+            T nn = 0;
+            for (int r = tid; r < n; r += JT) nn = fma(xz[r], xz[r], nn);
+            nn = jwarp_sum(nn);
+            if (lane == 0) s_val[warp] = nn;
+            __syncthreads();
+            T tot = 0;
+            for (int w = 0; w < NW; w++) tot += s_val[w];
+            __syncthreads();
+            const T inv = T(1) / sqrt(tot);
+            for (int r = tid; r < n; r += JT) xz[r] *= inv;
+            __syncthreads();
+        }
+        T *vt_g = Vt + mat * sVt;
+        for (int e = tid; e < n * n; e += JT) {
+            const int i = e % n, c = e / n;             // Vt(i, c) = W(c, perm i)
+            vt_g[i + (size_t) c * ldvt] = X[(size_t) s_perm[i] * ldx + c];
+        }
+        if (want_u) {
+            // Ur(:, i) = J(:, perm i): permute the columns in place through shared memory (X is free now)
+            __syncthreads();
+            for (int e = tid; e < n * n; e += JT) {
+                const int r = e % n, i = e / n;
+                X[(size_t) i * ldx + r] = J[(size_t) s_perm[i] * n + r];
+            }
+            __syncthreads();
+            for (int e = tid; e < n * n; e += JT) {
+                const int r = e % n, i = e / n;
+                J[(size_t) i * n + r] = X[(size_t) i * ldx + r];
+            }
+        }
+        if (tid == 0 && info) info[mat] = sweep >= 40 ? 1 : 0;
+        __syncthreads();
+    }
+}
+
 template<typename T> int internal_geqrf(gpub_ctx_t, int, size_t, size_t, T *, size_t, size_t, T *, size_t, size_t);
 template<> int internal_geqrf<double>(gpub_ctx_t c, int s, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sT, size_t b) { return gpub_geqrf_batched_f64(c, s, m, n, A, lda, sA, tau, sT, b); }
 template<> int internal_geqrf<float>(gpub_ctx_t c, int s, size_t m, size_t n, float *A, size_t lda, size_t sA, float *tau, size_t sT, size_t b) { return gpub_geqrf_batched_f32(c, s, m, n, A, lda, sA, tau, sT, b); }
@@ -96,7 +305,29 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         GPUB_LAUNCH_CHECK();
         return GPUB_OK;
     }
-    if (n > 32) return GPUB_ENOTSUP; // the Jacobi path is selected before this point once available
+    if (n > 32) {
+        // jacobi path: per-matrix scratch = [Ur n*n | tau n]
+        const size_t ldx = n | 1;
+        const size_t smem = (n * ldx + 2 * n) * sizeof(T) + n * sizeof(int) + 64;
+        if (smem > (size_t) ctx->max_smem_optin - 2048) return GPUB_ENOTSUP;
+        T *Urj = w, *tauj = w + n * n;
+        int e = internal_geqrf<T>(ctx, sidx, m, n, A, lda, sA, tauj, per, batch);
+        if (e) return e;
+        GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_rt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        const size_t cap = (size_t) ctx->sm_count * 2;
+        k_jacobi_rt<T><<<(unsigned) (batch < cap ? batch : cap), JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per,
+                                                                                      want_u ? 1 : 0, info, batch, (int) ldx);
+        GPUB_LAUNCH_CHECK();
+        if (want_u) {
+            size_t total = m * m * batch;
+            unsigned grid = (unsigned) (gpub_ceil_div(total, 256) < 8192 ? gpub_ceil_div(total, 256) : 8192);
+            k_init_u<T><<<grid, 256, 0, stream>>>((int) m, (int) n, Urj, per, U, ldu, sU, batch);
+            GPUB_LAUNCH_CHECK();
+            e = internal_ormqr<T>(ctx, sidx, 0, m, m, n, A, lda, sA, tauj, per, U, ldu, sU, batch);
+            if (e) return e;
+        }
+        return GPUB_OK;
+    }
 
     // tall path: per-matrix scratch = [G n*n | Ur n*n | tau n | scratch 7n]
     T *G = w, *Ur = w + n * n, *tau = w + 2 * n * n, *scr = tau + n;

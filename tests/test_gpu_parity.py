@@ -171,7 +171,9 @@ def _subspace_gap(U1, U2):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("m,n,batch,want_u", [(3, 2, 3, True), (8, 3, 4, True), (4, 3, 3, False), (3, 3, 5, True), (64, 16, 40, True),
-                                              (64, 32, 3, True), (200, 20, 3, True), (200, 20, 3, False), (500, 8, 2, True)])
+                                              (64, 32, 3, True), (200, 20, 3, True), (200, 20, 3, False), (500, 8, 2, True),
+                                              (128, 64, 2, True), (256, 40, 3, False), (100, 33, 2, True), (300, 128, 1, True),
+                                              (1024, 128, 2, False)])
 def test_gesvd_batched(gpu_ctx, oracle, dt, m, n, batch, want_u):
     from gputils_b200 import capi
     rng = np.random.default_rng(7 * m + n)
@@ -193,6 +195,30 @@ def test_gesvd_batched(gpu_ctx, oracle, dt, m, n, batch, want_u):
         assert rel_err(Un[:, :, :n] * Sn[:, None, :] @ Vn, A) <= tol
         for i in range(batch):   # orthogonal complement spans the same subspace as LAPACK's
             assert _subspace_gap(Un[i][:, n:], Uo[i][:, n:]) <= 1e3 * tol
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n", [(40, 12), (200, 48), (512, 128)])
+def test_gesvd_rank_deficient_factors_stay_orthogonal(gpu_ctx, oracle, dt, m, n):
+    """Rank-deficient input (duplicated columns, SURVEY.md 8d cfg4 variant): S has a numerically zero tail and
+    both factors must still be complete orthogonal matrices -- Nullspace takes the trailing columns of U."""
+    from gputils_b200 import capi
+    rng = np.random.default_rng(m + n)
+    A = rng.uniform(-1, 1, (2, m, n)).astype(dt)
+    dup = n // 8 + 1
+    A[:, :, n - dup:] = A[:, :, :dup]
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), True)
+    tol = 100 * TOL[np.dtype(dt)]
+    Sn = S.cpu().numpy().astype(np.float64); Un = host(U).astype(np.float64); Vn = host(Vt).astype(np.float64)
+    So, _, _ = oracle.gesvd_batched(A.astype(np.float64), False)
+    assert np.abs(Sn - So).max() <= tol * So.max()
+    assert np.all(Sn[:, n - dup:] <= 1e3 * tol * Sn[:, :1])
+    assert np.abs(Un.transpose(0, 2, 1) @ Un - np.eye(m)).max() <= tol
+    assert np.abs(Vn @ Vn.transpose(0, 2, 1) - np.eye(n)).max() <= tol
+    assert rel_err(Un[:, :, :n] * Sn[:, None, :] @ Vn, A) <= tol
+    # the trailing m - rank columns of U span the orthogonal complement of range(A)
+    r = n - dup
+    assert np.abs(Un[:, :, r:].transpose(0, 2, 1) @ A.astype(np.float64)).max() <= 1e3 * tol * So.max()
 
 
 @pytest.mark.parametrize("dt", DTYPES)
