@@ -56,7 +56,7 @@ _TYPED = {
 #: every symbol include/gputils_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = (
     ["gpub_version", "gpub_ctx_get", "gpub_ctx_ensure_streams", "gpub_ctx_num_streams", "gpub_ctx_stream",
-     "gpub_ctx_bind_stream", "gpub_ctx_sync", "gpub_ctx_sync_all", "gpub_ctx_device", "gpub_ctx_sm_count",
+     "gpub_ctx_bind_stream", "gpub_ctx_sync", "gpub_ctx_sync_all", "gpub_ctx_release", "gpub_ctx_device", "gpub_ctx_sm_count",
      "gpub_fill_ptr_table", "gpub_gesvd_batched_worksize_f64", "gpub_gesvd_batched_worksize_f32"]
     + [f"gpub_{n}_{s}" for n in _TYPED for s in ("f64", "f32")]
 )
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     lib.gpub_ctx_bind_stream.argtypes = [_vp, _int, _vp]
     lib.gpub_ctx_sync.argtypes = [_vp, _int]
     lib.gpub_ctx_sync_all.argtypes = [_vp]
+    lib.gpub_ctx_release.argtypes = [_vp]
     lib.gpub_ctx_device.argtypes = [_vp]
     lib.gpub_ctx_sm_count.argtypes = [_vp]
     lib.gpub_fill_ptr_table.argtypes = [_vp, _int, _vp, _sz, _sz, _vp]

@@ -19,6 +19,7 @@
 // Only the lower triangle is read and written: the strict upper triangle of A is never touched
 // (cuSOLVER semantics, SURVEY.md section 7 hard part 8). info[i] = first non-positive pivot (1-based) or 0.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -313,6 +314,143 @@ k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *
 }
 
 // ------------------------------------------------------------------------------------------
+// potrs, 32 < n <= 32*NB (NB = 2, 3, 4): k_potrs_blk<T, NB>, one matrix per CTA, same block ownership as
+// k_potrf_blk: one warp per 32 x 32 block of the lower triangle, lane = row of the block, the 32 entries of
+// that row in registers, read once from global memory (lower triangle only, coalesced column-wise).
+//   forward  L y = b, block column hb ascending:
+//     diagonal warp : t = b_hb - sum of the partial products left by its row of blocks, then the row-scaled
+//                     substitution of k_potrs_group (one shuffle + one FMA per step);
+//     warps below   : p = L(rb, hb) y_hb, one per-lane dot product against the broadcast y (LDS.128);
+//   backward L^T x = y, block column hb descending:
+//     diagonal warp : u = y_hb - partials, substitution on the columns of D^-1 L (transposed once through a
+//                     padded shared tile), x = D^-1 v;
+//     warps left of it (rb == hb): q = L(hb, h)^T x_hb. Lane r holds row r, so the 32 column sums are formed
+//                     by a 5-stage transpose-reduce butterfly (31 shuffles) instead of a second, transposed read.
+// Two CTA barriers per block column and direction. Rows / columns beyond n are an identity pad.
+// ------------------------------------------------------------------------------------------
+template<typename T, int NB> struct PotrsBlkMinB { static constexpr int value = NB == 2 ? 6 : (NB == 3 ? 3 : 2); };
+
+// p[c] summed over the 32 lanes, result for c == lane
+template<typename T>
+__device__ __forceinline__ T transpose_reduce32(T (&p)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; k++) {
+            const T keep = up ? p[o + k] : p[k];
+            const T send = up ? p[k] : p[o + k];
+            p[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return p[0];
+}
+
+template<typename T, int NB>
+__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrsBlkMinB<T, NB>::value)
+k_potrs_blk(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, size_t strideB, size_t batch) {
+    constexpr int NW = NB * (NB + 1) / 2;
+    __shared__ __align__(16) T s_x[NB * 32];      // right-hand side -> y -> x
+    __shared__ __align__(16) T s_part[NW][32];    // partial products, one slot per block
+    __shared__ T s_t[NB][32][33];                 // diagonal blocks of D^-1 L for the transposed read
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int rb = 0;
+    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
+    const int h = warp - rb * (rb + 1) / 2;
+    const bool diag = rb == h;
+    const int row = 32 * rb + lane;
+    using V2 = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
+    constexpr int VN = 16 / sizeof(T);
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        const T *l_g = L + mat * strideL;
+        T *b_g = b + mat * strideB;
+        T l[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int col = 32 * h + c;
+            l[c] = (row < n && col <= row) ? l_g[row + (size_t) col * ldl] : T(row == col ? 1 : 0);
+        }
+        if (threadIdx.x < NB * 32) s_x[threadIdx.x] = threadIdx.x < n ? b_g[threadIdx.x] : T(0);
+        T dinv = T(1);
+        if (diag) {
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+                if (c == lane) dinv = T(1) / l[c];
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                l[c] = c < lane ? l[c] * dinv : T(0);   // strictly lower part of D^-1 L
+                s_t[rb][lane][c] = l[c];
+            }
+        }
+        __syncthreads();
+        // ---- forward ----
+#pragma unroll 1
+        for (int hb = 0; hb < NB; hb++) {
+            if (diag && rb == hb) {
+                T x = s_x[32 * hb + lane];
+                for (int hp = 0; hp < hb; hp++) x -= s_part[hb * (hb + 1) / 2 + hp][lane];
+                x *= dinv;
+#pragma unroll
+                for (int j = 0; j < 31; j++) {
+                    const T yj = __shfl_sync(0xffffffffu, x, j);
+                    x = fma(-l[j], yj, x);
+                }
+                s_x[32 * hb + lane] = x;
+            }
+            __syncthreads();
+            if (h == hb && rb > hb) {
+                T p0 = 0, p1 = 0;
+#pragma unroll
+                for (int c = 0; c < 32; c += VN) {
+                    const V2 v = *reinterpret_cast<const V2 *>(&s_x[32 * hb + c]);
+                    T y[VN];
+                    if constexpr (sizeof(T) == 8) { y[0] = v.x; y[1] = v.y; }
+                    else { y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w; }
+#pragma unroll
+                    for (int e = 0; e < VN; e++) {
+                        if (e & 1) p1 = fma(l[c + e], y[e], p1);
+                        else p0 = fma(l[c + e], y[e], p0);
+                    }
+                }
+                s_part[warp][lane] = p0 + p1;
+            }
+            __syncthreads();
+        }
+        // ---- backward ----
+        if (diag) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) l[r] = s_t[rb][r][lane]; // column `lane` of D^-1 L (zero on and above the diagonal)
+        }
+#pragma unroll 1
+        for (int hb = NB - 1; hb >= 0; hb--) {
+            if (diag && rb == hb) {
+                T x = s_x[32 * hb + lane];
+                for (int rp = hb + 1; rp < NB; rp++) x -= s_part[rp * (rp + 1) / 2 + hb][lane];
+#pragma unroll
+                for (int jj = 31; jj > 0; jj--) {
+                    const T vj = __shfl_sync(0xffffffffu, x, jj);
+                    x = fma(-l[jj], vj, x);
+                }
+                x *= dinv;
+                s_x[32 * hb + lane] = x;
+            }
+            __syncthreads();
+            if (rb == hb && h < hb) {
+                const T xr = s_x[32 * hb + lane];
+                T p[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) p[c] = l[c] * xr;
+                s_part[warp][lane] = transpose_reduce32<T>(p, lane);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < n) b_g[threadIdx.x] = s_x[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // potrs, any n: one CTA per matrix, rhs in shared memory, coalesced column sweeps of L
 // ------------------------------------------------------------------------------------------
 template<typename T>
@@ -429,6 +567,12 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
         }
 #undef GPUB_POTRS_LAUNCH
 #undef GPUB_POTRS_CASE
+    } else if (n <= 128) {
+        const size_t cap = (size_t) ctx->sm_count * 8;
+        const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+        if (n <= 64) k_potrs_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
+        else if (n <= 96) k_potrs_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
+        else k_potrs_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
     } else {
         const size_t smem = n * sizeof(T);
         if (smem > 48 * 1024)

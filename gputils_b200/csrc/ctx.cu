@@ -128,6 +128,23 @@ int gpub_ctx_sync_all(gpub_ctx_t ctx) {
     return GPUB_OK;
 }
 
+int gpub_ctx_release(gpub_ctx_t ctx) {
+    if (!ctx) return GPUB_EINVAL;
+    gpub_device_guard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int first_err = GPUB_OK;
+    auto keep = [&](cudaError_t e) { if (e != cudaSuccess && first_err == GPUB_OK) first_err = (int) e; };
+    for (auto &s: ctx->slots) {
+        if (s.stream) keep(cudaStreamSynchronize(s.stream));
+        if (s.d_scratch) keep(cudaFree(s.d_scratch));
+        if (s.d_counter) keep(cudaFree(s.d_counter));
+        if (s.h_result) keep(cudaFreeHost(s.h_result));
+        if (s.stream && s.owned) keep(cudaStreamDestroy(s.stream));
+        s = gpub_stream_slot();   // recreated lazily if the slot is used again
+    }
+    return first_err;
+}
+
 int gpub_ctx_device(gpub_ctx_t ctx) { return ctx ? ctx->device : -1; }
 
 int gpub_ctx_sm_count(gpub_ctx_t ctx) { return ctx ? ctx->sm_count : 0; }

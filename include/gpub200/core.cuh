@@ -160,6 +160,9 @@ private:
     }
 
     ~Session() {
+        /* like the reference's destructor (tensor.cuh:168-173), which destroys its handles and streams:
+         * hands the streams and the per-stream scratch back, so leak checkers see a clean exit */
+        if (m_ctx) gpub_ctx_release(m_ctx);
 #ifdef GPUTILS_B200_ENABLE_CUBLAS_HANDLES
         for (auto &h: m_cublasHandles) if (h) cublasDestroy(h);
         for (auto &h: m_cusolverHandles) if (h) cusolverDnDestroy(h);

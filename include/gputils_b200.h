@@ -57,6 +57,9 @@ int gpub_ctx_bind_stream(gpub_ctx_t ctx, int sidx, void *cuda_stream);
 /* ref: tensor.cuh:232-246 */
 int gpub_ctx_sync(gpub_ctx_t ctx, int sidx);
 int gpub_ctx_sync_all(gpub_ctx_t ctx);
+/* ref: tensor.cuh:168-173 (~Session destroys its handles): synchronise, then free the streams this context
+ * owns and the per-stream scratch. The context stays valid; slots are recreated lazily if used again. */
+int gpub_ctx_release(gpub_ctx_t ctx);
 int gpub_ctx_device(gpub_ctx_t ctx);
 int gpub_ctx_sm_count(gpub_ctx_t ctx);
 
