@@ -114,7 +114,7 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 // Three CTA barriers per block column instead of two per column. Rows / columns beyond n are an identity pad.
 // ------------------------------------------------------------------------------------------
 // resident CTAs per SM the register allocation is tuned for
-template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : (sizeof(T) == 8 ? 1 : 2)); };
+template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : 2); };
 
 template<typename T, int NB>
 __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_blk(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
@@ -437,11 +437,11 @@ k_potrs_blk(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, si
             }
             __syncthreads();
             if (rb == hb && h < hb) {
+                // each off-diagonal warp comes here exactly once per matrix, so its row can be consumed in place
                 const T xr = s_x[32 * hb + lane];
-                T p[32];
 #pragma unroll
-                for (int c = 0; c < 32; c++) p[c] = l[c] * xr;
-                s_part[warp][lane] = transpose_reduce32<T>(p, lane);
+                for (int c = 0; c < 32; c++) l[c] *= xr;
+                s_part[warp][lane] = transpose_reduce32<T>(l, lane);
             }
             __syncthreads();
         }

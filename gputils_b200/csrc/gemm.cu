@@ -637,6 +637,102 @@ bool try_dgemm_frag<double, 32>(gpub_ctx_t ctx, cudaStream_t stream, double alph
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32, N = 32, dense batch: k_sgemm32_rt -- one warp per matrix, 4 x 8 register tile per lane.
+// k_gemm_col<float, 32> (lane = column, 8 broadcast LDS.128 of A per 32 FFMA) is bound by the shared-memory
+// to register-file path; here lane (rg, cg) owns rows 4rg..4rg+3 and columns cg, cg+4, ..., cg+28, so four
+// k-steps cost 4 LDS.128 of A (rows contiguous) + 8 LDS.128 of B (4 consecutive k of one column) for 128 FFMA.
+// A and B land in the warp's double-buffered shared slot through cp.async (B columns padded to 36 floats:
+// the four column groups of a quarter-warp phase hit different banks); the next matrix is in flight while the
+// current one is multiplied; C leaves as 128-bit stores that cover whole 128-byte lines. No CTA barrier.
+// ------------------------------------------------------------------------------------------
+constexpr int S32_LDB = 36;
+constexpr int S32_SLOT = 32 * 32 + 32 * S32_LDB; // floats per buffer: A then padded B
+constexpr int S32_WARPS = 4;
+
+__global__ void __launch_bounds__(S32_WARPS * 32, 3) k_sgemm32_rt(float alpha, const float *__restrict__ A, const float *__restrict__ B,
+                                                                   float beta, float *C, size_t batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float (*s_buf)[2][S32_SLOT] = reinterpret_cast<float (*)[2][S32_SLOT]>(smem_raw); // [warp][buffer][slot]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = lane & 7, cg = lane >> 3;
+    const size_t nwarps = (size_t) gridDim.x * S32_WARPS;
+    const size_t wg = (size_t) blockIdx.x * S32_WARPS + warp;
+
+    auto issue = [&](size_t mat, int buf) {
+        float *sa = s_buf[warp][buf], *sb = sa + 1024;
+        const float *a = A + mat * 1024, *b = B + mat * 1024;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            const int e = (lane + 32 * p) * 4;
+            cp_async16_ca(sa + e, a + e);
+            cp_async16_ca(sb + (e >> 5) * S32_LDB + (e & 31), b + e);
+        }
+        cp_async_commit_grp();
+    };
+
+    if (wg < batch) issue(wg, 0);
+    int buf = 0;
+    for (size_t mat = wg; mat < batch; mat += nwarps, buf ^= 1) {
+        if (mat + nwarps < batch) {
+            issue(mat + nwarps, buf ^ 1);
+            cp_async_wait_grp<1>();
+        } else {
+            cp_async_wait_grp<0>();
+        }
+        __syncwarp();
+        const float *sa = s_buf[warp][buf] + 4 * rg, *sb = s_buf[warp][buf] + 1024 + cg * S32_LDB;
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[j][r] = 0.f;
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            float4 bv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) bv[j] = *reinterpret_cast<const float4 *>(sb + 4 * j * S32_LDB + k0);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const float4 av = *reinterpret_cast<const float4 *>(sa + (k0 + kk) * 32);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float bk = kk == 0 ? bv[j].x : (kk == 1 ? bv[j].y : (kk == 2 ? bv[j].z : bv[j].w));
+                    acc[j][0] = fmaf(av.x, bk, acc[j][0]);
+                    acc[j][1] = fmaf(av.y, bk, acc[j][1]);
+                    acc[j][2] = fmaf(av.z, bk, acc[j][2]);
+                    acc[j][3] = fmaf(av.w, bk, acc[j][3]);
+                }
+            }
+        }
+        __syncwarp(); // every lane is done with slot `buf` before the copy two iterations ahead refills it
+        float *c = C + mat * 1024 + cg * 32 + 4 * rg;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float4 *p = reinterpret_cast<float4 *>(c + 4 * j * 32);
+            float4 o = make_float4(alpha * acc[j][0], alpha * acc[j][1], alpha * acc[j][2], alpha * acc[j][3]);
+            if (beta != 0.f) {
+                const float4 old = *p;
+                o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+            }
+            *p = o;
+        }
+    }
+}
+
+template<typename T>
+bool try_sgemm32(gpub_ctx_t, cudaStream_t, T, const T *, const T *, T, T *, size_t, int *) { return false; }
+template<>
+bool try_sgemm32<float>(gpub_ctx_t ctx, cudaStream_t stream, float alpha, const float *A, const float *B, float beta, float *C, size_t batch, int *err) {
+    const size_t smem = sizeof(float) * S32_WARPS * 2 * S32_SLOT;
+    cudaError_t e = cudaFuncSetAttribute(k_sgemm32_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) { *err = (int) e; return true; }
+    const size_t want = gpub_ceil_div(batch, (size_t) S32_WARPS), cap = (size_t) ctx->sm_count * 3;
+    k_sgemm32_rt<<<(unsigned) (want < cap ? want : cap), S32_WARPS * 32, smem, stream>>>(alpha, A, B, beta, C, batch);
+    *err = GPUB_OK;
+    return true;
+}
+
 template<typename T> struct UseDmma { static constexpr bool value = false; };
 template<> struct UseDmma<double> { static constexpr bool value = true; };
 
@@ -690,6 +786,14 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
                 return launch_col<T, 16>(ctx, stream, alpha, A, B, beta, C, batch);
             case 32:
                 if (try_dgemm_frag<T, 32>(ctx, stream, alpha, A, B, beta, C, batch)) { GPUB_LAUNCH_CHECK(); return GPUB_OK; }
+                {
+                    int e32 = GPUB_OK;
+                    if (try_sgemm32<T>(ctx, stream, alpha, A, B, beta, C, batch, &e32)) {
+                        if (e32 != GPUB_OK) return e32;
+                        GPUB_LAUNCH_CHECK();
+                        return GPUB_OK;
+                    }
+                }
                 return launch_col<T, 32>(ctx, stream, alpha, A, B, beta, C, batch);
             default: break;
         }
