@@ -357,6 +357,337 @@ __global__ void __launch_bounds__(QT) k_geqrf_wy(int m, int n, T *A, size_t lda,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp64 tall-skinny QR on the FP64 tensor pipe: k_geqrf_tc<RPT>, one matrix per CTA, 512 threads, m <= 512 * RPT.
+// Compact WY with panels of 16 columns (cfg4: 1024 x 128, 8 panels):
+//   panel   : every thread keeps its RPT rows of the 16 panel columns in REGISTERS. One CTA barrier per column: the
+//             dots x^T a_c of the unscaled pivot column with itself and with the columns to its right are reduced
+//             together (transpose-reduce butterfly per warp, 16 per-warp partials through shared memory), then every
+//             warp derives beta, tau, 1/(alpha - beta) and the update coefficients tau (a_c[j] + scale x^T a_c)
+//             redundantly, so no second barrier is needed to broadcast them.
+//   T       : G = V^T V by DMMA (m8n8k4) tiles over 16 row ranges, then T(i, j) = -tau_j sum_k T(i, k) G(k, j), one
+//             lane per row of T (no cross-lane dependency).
+//   trailing: A2 <- A2 - V (T^T (V^T A2)). One warp per block of 8 trailing columns. Pass 1: W = V^T A2 with V
+//             fragments from shared memory (stored [column][row], leading dimension = 4 mod 16: both fragment
+//             patterns are bank-conflict free) and A2 fragments straight from global memory (every LDG.64 of the warp
+//             covers whole sectors), two independent accumulator sets. W' = -T^T W in the warp's own scratch.
+//             Pass 2: A2 tile (8 x 8, DMMA accumulator layout) += V W', 4 DMMA per tile, read and written in place.
+//             Passes of different warps are independent: no CTA barrier inside the trailing update.
+// Output is LAPACK's (R on / above the diagonal, reflectors below, tau), same dlarfg rule as the other kernels.
+// ------------------------------------------------------------------------------------------
+constexpr int TCQ_THREADS = 512;
+constexpr int TCQ_WARPS = TCQ_THREADS / 32;
+constexpr int TCQ_NB = 16;
+constexpr int TCQ_LDW = 20; // scratch leading dimension, = 4 mod 16
+constexpr int TCQ_SCR = 2 * 8 * TCQ_LDW; // per-warp scratch (doubles): W and W' of one block of 8 columns; >= 256 for the Gram partials
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// v[0..P-1] per lane -> v[0] = sum over the 32 lanes of value number lane / (32 / P)   (P a power of two <= 32)
+template<int P, int O>
+struct TReduce {
+    static __device__ __forceinline__ void run(double *v, int lane) {
+        if constexpr (P > 1) {
+            constexpr int H = P / 2;
+            const bool up = (lane & O) != 0;
+#pragma unroll
+            for (int k = 0; k < H; k++) {
+                const double keep = up ? v[H + k] : v[k];
+                const double send = up ? v[k] : v[H + k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+        }
+        if constexpr (O > 1) TReduce<(P > 1 ? P / 2 : 1), O / 2>::run(v, lane);
+    }
+};
+
+__host__ __device__ constexpr int tcq_pow2ceil(int x) { return x <= 1 ? 1 : (x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16))); }
+
+struct TcqShared {
+    double *Vs;      // [16][ldv]
+    double *Ts;      // [16][17]
+    double *Gs;      // [16][17]
+    double *red;     // [2][16 warps][16]
+    double *piv;     // [2][16]
+    double *taus;    // [16]
+    double *scr;     // [16 warps][TCQ_SCR]: W and W' per warp (also the per-warp 16 x 16 partial Gram tiles)
+};
+
+template<int RPT, int JJ>
+__device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const int (&rr)[RPT], const TcqShared &sh, int warp, int lane,
+                                                 double *tau_g, int tau_ok_upto) {
+    constexpr int NV = TCQ_NB - JJ;          // values reduced: column JJ with itself and with columns JJ+1..15
+    constexpr int P = tcq_pow2ceil(NV);
+    const int buf = JJ & 1;
+    double part[P];
+#pragma unroll
+    for (int s = 0; s < P; s++) part[s] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        const double x = rr[i] > JJ ? p[JJ][i] : 0.0;
+#pragma unroll
+        for (int s = 0; s < NV; s++) part[s] = fma(x, p[JJ + s][i], part[s]);
+    }
+    TReduce<P, 16>::run(part, lane);
+    if ((lane & (32 / P - 1)) == 0) sh.red[(buf * TCQ_WARPS + warp) * TCQ_NB + lane / (32 / P)] = part[0];
+    if (rr[0] == JJ) {                       // the owner of the pivot row publishes it
+#pragma unroll
+        for (int s = 0; s < NV; s++) sh.piv[buf * TCQ_NB + s] = p[JJ + s][0];
+    }
+    __syncthreads();
+    // lane l < NV: total of value l (column JJ + l) and the pivot-row entry of that column
+    double tot = 0.0, tot2 = 0.0, pv = 0.0;
+    if (lane < NV) {
+#pragma unroll
+        for (int w = 0; w < TCQ_WARPS; w += 2) {
+            tot += sh.red[(buf * TCQ_WARPS + w) * TCQ_NB + lane];
+            tot2 += sh.red[(buf * TCQ_WARPS + w + 1) * TCQ_NB + lane];
+        }
+        tot += tot2;
+        pv = sh.piv[buf * TCQ_NB + lane];
+    }
+    const double xnorm2 = __shfl_sync(0xffffffffu, tot, 0);
+    const double alpha = __shfl_sync(0xffffffffu, pv, 0);
+    double tau = 0.0, scale = 0.0, beta = alpha;
+    if (xnorm2 != 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, xnorm2));
+        beta = alpha >= 0.0 ? -nrm : nrm;
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    const double coef = tau != 0.0 ? tau * fma(scale, tot, pv) : 0.0;      // lane l >= 1: tau * v^T a_(JJ+l)
+    double v[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) v[i] = rr[i] > JJ ? p[JJ][i] * scale : (rr[i] == JJ ? 1.0 : 0.0);
+#pragma unroll
+    for (int s = 1; s < NV; s++) {
+        const double cf = __shfl_sync(0xffffffffu, coef, s);
+#pragma unroll
+        for (int i = 0; i < RPT; i++) p[JJ + s][i] = fma(-cf, v[i], p[JJ + s][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; i++) p[JJ][i] = rr[i] > JJ ? v[i] : (rr[i] == JJ ? beta : p[JJ][i]);
+    if (warp == 0 && lane == 0) {
+        sh.taus[JJ] = tau;
+        if (JJ < tau_ok_upto) tau_g[JJ] = tau;
+    }
+    if constexpr (JJ + 1 < TCQ_NB) tcq_panel_column<RPT, JJ + 1>(p, rr, sh, warp, lane, tau_g, tau_ok_upto);
+}
+
+template<int RPT>
+__global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, double *A, size_t lda, size_t sA, double *tau, size_t sTau, size_t batch,
+                                                              int ldv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TcqShared sh;
+    sh.Vs = reinterpret_cast<double *>(smem_raw);
+    sh.Ts = sh.Vs + (size_t) TCQ_NB * ldv;
+    sh.Gs = sh.Ts + TCQ_NB * 17;
+    sh.red = sh.Gs + TCQ_NB * 17;
+    sh.piv = sh.red + 2 * TCQ_WARPS * TCQ_NB;
+    sh.taus = sh.piv + 2 * TCQ_NB;
+    sh.scr = sh.taus + TCQ_NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int kmax = n < m ? n : m;
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        double *a_g = A + mat * sA;
+        double *tau_g = tau + mat * sTau;
+        for (int j0 = 0; j0 < kmax; j0 += TCQ_NB) {
+            const int nb = (kmax - j0) < TCQ_NB ? (kmax - j0) : TCQ_NB;
+            const int mj = m - j0;                       // rows of the panel
+            const int mj4 = (mj + 3) & ~3;
+            // ---- panel into registers: thread owns panel rows tid, tid + 512, ... ----
+            double p[TCQ_NB][RPT];
+            int rr[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                rr[i] = tid + TCQ_THREADS * i;
+                const bool ok = rr[i] < mj;
+#pragma unroll
+                for (int c = 0; c < TCQ_NB; c++) p[c][i] = (ok && c < nb) ? a_g[(size_t) (j0 + rr[i]) + (size_t) (j0 + c) * lda] : 0.0;
+                if (!ok) rr[i] = -1;                     // never "below the pivot"
+            }
+            tcq_panel_column<RPT, 0>(p, rr, sh, warp, lane, tau_g + j0, nb);
+            // ---- factored panel back to global memory; explicit V (unit diagonal, zeros above) to shared memory ----
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                const int r = tid + TCQ_THREADS * i;
+                if (r < mj4) {
+#pragma unroll
+                    for (int c = 0; c < TCQ_NB; c++) {
+                        if (r < mj && c < nb) a_g[(size_t) (j0 + r) + (size_t) (j0 + c) * lda] = p[c][i];
+                        sh.Vs[(size_t) c * ldv + r] = r < mj ? (r > c ? p[c][i] : (r == c ? 1.0 : 0.0)) : 0.0;
+                    }
+                }
+            }
+            const int ntrail = n - (j0 + TCQ_NB);
+            if (ntrail <= 0) { __syncthreads(); continue; }
+            __syncthreads();
+            // ---- G = V^T V: each warp one row range, upper three 8 x 8 tiles ----
+            {
+                const int kr = ((mj4 / 4 + TCQ_WARPS - 1) / TCQ_WARPS) * 4;
+                const int r0 = warp * kr, r1 = (r0 + kr) < mj4 ? (r0 + kr) : mj4;
+                double g00[2] = {0, 0}, g01[2] = {0, 0}, g11[2] = {0, 0};
+                const double *v0 = sh.Vs + (size_t) g * ldv + q, *v1 = sh.Vs + (size_t) (8 + g) * ldv + q;
+                for (int r = r0; r < r1; r += 4) {
+                    const double f0 = v0[r], f1 = v1[r];
+                    dmma884(g00[0], g00[1], f0, f0);
+                    dmma884(g01[0], g01[1], f0, f1);
+                    dmma884(g11[0], g11[1], f1, f1);
+                }
+                double *gp = sh.scr + (size_t) warp * TCQ_SCR;
+                gp[g * 16 + 2 * q] = g00[0]; gp[g * 16 + 2 * q + 1] = g00[1];
+                gp[g * 16 + 8 + 2 * q] = g01[0]; gp[g * 16 + 8 + 2 * q + 1] = g01[1];
+                gp[(8 + g) * 16 + 8 + 2 * q] = g11[0]; gp[(8 + g) * 16 + 8 + 2 * q + 1] = g11[1];
+            }
+            __syncthreads();
+            if (tid < 256) {
+                const int i = tid >> 4, j = tid & 15;
+                if (i < j && !(i >= 8 && j < 8)) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < TCQ_WARPS; w++) acc += sh.scr[(size_t) w * TCQ_SCR + tid];
+                    sh.Gs[i * 17 + j] = acc;
+                }
+            }
+            __syncthreads();
+            if (warp == 0 && lane < TCQ_NB) {
+                double trow[TCQ_NB];
+#pragma unroll
+                for (int j = 0; j < TCQ_NB; j++) {
+                    const double tj = sh.taus[j];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < j; k++)
+                        if (k >= lane) acc = fma(trow[k], sh.Gs[k * 17 + j], acc);
+                    trow[j] = j == lane ? tj : (j > lane ? -tj * acc : 0.0);
+                    sh.Ts[lane * 17 + j] = trow[j];
+                }
+            }
+            __syncthreads();
+            // ---- trailing update, one warp per block of 8 columns ----
+            const int ncb = (ntrail + 7) / 8;
+            double *ws = sh.scr + (size_t) warp * TCQ_SCR, *wp = ws + 8 * TCQ_LDW;
+            for (int cb = warp; cb < ncb; cb += TCQ_WARPS) {
+                const int c0 = j0 + TCQ_NB + 8 * cb;
+                // pass 1: W = V^T A2 (16 x 8)
+                double w0[2] = {0, 0}, w1[2] = {0, 0}, x0[2] = {0, 0}, x1[2] = {0, 0};
+                {
+                    const bool col_ok = c0 + g < n;
+                    const double *a2 = a_g + (size_t) j0 + (size_t) (col_ok ? c0 + g : c0) * lda + q;
+                    const double *v0 = sh.Vs + (size_t) g * ldv + q, *v1 = sh.Vs + (size_t) (8 + g) * ldv + q;
+                    int r = 0;
+                    for (; r + 16 <= mj; r += 16) {
+                        double bfr[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) bfr[u] = col_ok ? a2[r + 4 * u] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; u += 2) {
+                            dmma884(w0[0], w0[1], v0[r + 4 * u], bfr[u]);
+                            dmma884(w1[0], w1[1], v1[r + 4 * u], bfr[u]);
+                            dmma884(x0[0], x0[1], v0[r + 4 * u + 4], bfr[u + 1]);
+                            dmma884(x1[0], x1[1], v1[r + 4 * u + 4], bfr[u + 1]);
+                        }
+                    }
+                    for (; r < mj4; r += 4) {
+                        const double bf = (col_ok && r + q < mj) ? a2[r] : 0.0;
+                        dmma884(w0[0], w0[1], v0[r], bf);
+                        dmma884(w1[0], w1[1], v1[r], bf);
+                    }
+                    w0[0] += x0[0]; w0[1] += x0[1]; w1[0] += x1[0]; w1[1] += x1[1];
+                }
+                // W (accumulator layout: rows g / 8 + g, columns 2q, 2q + 1) -> ws[column][k]
+                __syncwarp();
+                ws[(2 * q) * TCQ_LDW + g] = w0[0]; ws[(2 * q + 1) * TCQ_LDW + g] = w0[1];
+                ws[(2 * q) * TCQ_LDW + 8 + g] = w1[0]; ws[(2 * q + 1) * TCQ_LDW + 8 + g] = w1[1];
+                __syncwarp();
+                // W' = -T^T W: lane -> column c = lane & 7, rows i = (lane >> 3) + 4u
+                {
+                    const int c = lane & 7;
+                    double wc[TCQ_NB];
+#pragma unroll
+                    for (int k = 0; k < TCQ_NB; k++) wc[k] = ws[c * TCQ_LDW + k];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (lane >> 3) + 4 * u;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < TCQ_NB; k++)
+                            if (k <= i) acc = fma(sh.Ts[k * 17 + i], wc[k], acc);
+                        wp[c * TCQ_LDW + i] = -acc;
+                    }
+                }
+                __syncwarp();
+                // pass 2: A2 tile += V W'
+                double bw[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) bw[s4] = wp[g * TCQ_LDW + 4 * s4 + q];
+                const bool c_ok0 = c0 + 2 * q < n, c_ok1 = c0 + 2 * q + 1 < n;
+                double *t0 = a_g + (size_t) j0 + (size_t) (c0 + 2 * q) * lda + g;
+                double *t1 = t0 + lda;
+                const double *va = sh.Vs + (size_t) q * ldv + g;
+                const int ntile = (mj + 7) / 8;
+                int rt = 0;
+                for (; rt + 4 <= ntile && 8 * (rt + 4) <= mj; rt += 4) {
+                    double c[4][2];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        c[u][0] = c_ok0 ? t0[8 * (rt + u)] : 0.0;
+                        c[u][1] = c_ok1 ? t1[8 * (rt + u)] : 0.0;
+                    }
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++) dmma884(c[u][0], c[u][1], va[(size_t) (4 * s4) * ldv + 8 * (rt + u)], bw[s4]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (c_ok0) t0[8 * (rt + u)] = c[u][0];
+                        if (c_ok1) t1[8 * (rt + u)] = c[u][1];
+                    }
+                }
+                for (; rt < ntile; rt++) {
+                    const bool r_ok = 8 * rt + g < mj;
+                    double c[2];
+                    c[0] = (r_ok && c_ok0) ? t0[8 * rt] : 0.0;
+                    c[1] = (r_ok && c_ok1) ? t1[8 * rt] : 0.0;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) dmma884(c[0], c[1], r_ok ? va[(size_t) (4 * s4) * ldv + 8 * rt] : 0.0, bw[s4]);
+                    if (r_ok && c_ok0) t0[8 * rt] = c[0];
+                    if (r_ok && c_ok1) t1[8 * rt] = c[1];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template<typename T>
+bool try_geqrf_tc(gpub_ctx_t, cudaStream_t, size_t, size_t, T *, size_t, size_t, T *, size_t, size_t, int *) { return false; }
+template<>
+bool try_geqrf_tc<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sTau,
+                          size_t batch, int *err) {
+    if (m > 1024 || m < 64 || n < 16) return false;
+    const size_t ldv = (m + 15) / 16 * 16 + 4;
+    const size_t smem = (TCQ_NB * ldv + 2 * TCQ_NB * 17 + 2 * TCQ_WARPS * TCQ_NB + 2 * TCQ_NB + TCQ_NB + (size_t) TCQ_WARPS * TCQ_SCR) * sizeof(double);
+    if (smem > (size_t) ctx->max_smem_optin) return false;
+    const unsigned grid = (unsigned) (batch < (size_t) ctx->sm_count ? batch : (size_t) ctx->sm_count);
+    cudaError_t e;
+    if (m <= 512) {
+        e = cudaFuncSetAttribute(k_geqrf_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess) k_geqrf_tc<1><<<grid, TCQ_THREADS, smem, stream>>>((int) m, (int) n, A, lda, sA, tau, sTau, batch, (int) ldv);
+    } else {
+        e = cudaFuncSetAttribute(k_geqrf_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess) k_geqrf_tc<2><<<grid, TCQ_THREADS, smem, stream>>>((int) m, (int) n, A, lda, sA, tau, sTau, batch, (int) ldv);
+    }
+    *err = e == cudaSuccess ? GPUB_OK : (int) e;
+    return true;
+}
+
 // C <- Q^T C (trans) or Q C: every warp owns whole columns of C, so no CTA-wide synchronisation
 template<typename T>
 __global__ void __launch_bounds__(QT) k_ormqr_cta(int trans, int m, int ncols, int k, const T *__restrict__ A, size_t lda, size_t sA,
@@ -534,6 +865,14 @@ int geqrf_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda
     GPUB_ENTER(ctx, sidx);
     const size_t bytes = qr_smem_bytes<T>(m, n, false);
     const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 2048 ? 1 : 0;
+    if (m >= 256 && n >= 32) {
+        int etc = GPUB_OK;
+        if (try_geqrf_tc<T>(ctx, stream, m, n, A, lda, sA, tau, sTau, batch, &etc)) {
+            if (etc != GPUB_OK) return etc;
+            GPUB_LAUNCH_CHECK();
+            return GPUB_OK;
+        }
+    }
     if (!use_smem || (m >= 256 && n >= 32)) {
         // blocked compact-WY: the widest panel whose [NBQ][m] block fits in shared memory
         const size_t ldv = (m + 3) / 4 * 4 + 4;

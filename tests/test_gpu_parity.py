@@ -134,7 +134,8 @@ def test_gels_batched(gpu_ctx, oracle, dt, m, n, batch):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("m,n,batch", [(4, 3, 1), (20, 3, 1), (64, 16, 9), (128, 128, 2), (300, 20, 3), (1024, 128, 2)])
+@pytest.mark.parametrize("m,n,batch", [(4, 3, 1), (20, 3, 1), (64, 16, 9), (128, 128, 2), (300, 20, 3), (1024, 128, 2),
+                                       (1024, 128, 150), (1000, 100, 3), (513, 37, 2), (257, 32, 5), (512, 48, 2), (300, 300, 1)])
 def test_geqrf_ormqr_trsv(gpu_ctx, oracle, dt, m, n, batch):
     import torch
     from gputils_b200 import capi
