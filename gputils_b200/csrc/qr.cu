@@ -375,14 +375,42 @@ __global__ void __launch_bounds__(QT) k_geqrf_wy(int m, int n, T *A, size_t lda,
 //             Passes of different warps are independent: no CTA barrier inside the trailing update.
 // Output is LAPACK's (R on / above the diagonal, reflectors below, tau), same dlarfg rule as the other kernels.
 // ------------------------------------------------------------------------------------------
+#ifdef GPUB_TCQ_PROFILE
+__device__ unsigned long long g_tcq_prof[8];
+#define TCQ_T(idx) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_tcq_prof[idx], (unsigned long long) (t_ - tcq_t0)); tcq_t0 = t_; } } while (0)
+#else
+#define TCQ_T(idx) do { } while (0)
+#endif
 constexpr int TCQ_THREADS = 512;
 constexpr int TCQ_WARPS = TCQ_THREADS / 32;
 constexpr int TCQ_NB = 16;
+#ifndef GPUB_TCQ_D1
+#define GPUB_TCQ_D1 4
+#endif
+#ifndef GPUB_TCQ_D2
+#define GPUB_TCQ_D2 1
+#endif
+constexpr int TCQ_D1 = GPUB_TCQ_D1;   // pass 1: depth of the register pipeline (chunks of 8 rows)
+constexpr int TCQ_D2 = GPUB_TCQ_D2;   // pass 2: depth of the register pipeline (blocks of 16 rows)
+constexpr int TCQ_NSL = 2;  // column blocks (slots) per warp in one chunk of the trailing update
 constexpr int TCQ_LDW = 20; // scratch leading dimension, = 4 mod 16
-constexpr int TCQ_SCR = 2 * 8 * TCQ_LDW; // per-warp scratch (doubles): W and W' of one block of 8 columns; >= 256 for the Gram partials
+constexpr int TCQ_PART = 4 * 16 * 128;      // doubles: partial W of 4 row groups x 16 column blocks (>= 16 x 256 for the Gram partials)
+constexpr int TCQ_WP = 16 * 8 * TCQ_LDW;    // doubles: W' of 16 column blocks
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
 }
 
 // v[0..P-1] per lane -> v[0] = sum over the 32 lanes of value number lane / (32 / P)   (P a power of two <= 32)
@@ -407,14 +435,26 @@ struct TReduce {
 
 __host__ __device__ constexpr int tcq_pow2ceil(int x) { return x <= 1 ? 1 : (x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16))); }
 
+// shared-memory layout: fixed-size regions first, so every address is base + compile-time offset (one live pointer)
+constexpr int TCQ_OFF_TS = 0;                                  // [16][17]  T
+constexpr int TCQ_OFF_GS = TCQ_OFF_TS + TCQ_NB * 17;           // [16][17]  G = V^T V
+constexpr int TCQ_OFF_RED = TCQ_OFF_GS + TCQ_NB * 17;          // [2][16 warps][16] per-warp partial dots
+constexpr int TCQ_OFF_PIV = TCQ_OFF_RED + 2 * TCQ_WARPS * TCQ_NB; // [2][16] pivot row
+constexpr int TCQ_OFF_TAU = TCQ_OFF_PIV + 2 * TCQ_NB;          // [16]
+constexpr int TCQ_OFF_PART = TCQ_OFF_TAU + TCQ_NB;             // [4 row groups][16 column blocks][8 columns][16] partial W
+                                                               // (also the 16 per-warp 16 x 16 partial Gram tiles)
+constexpr int TCQ_OFF_WP = TCQ_OFF_PART + TCQ_PART;            // [16 column blocks][8][TCQ_LDW]  W' = -T^T W
+constexpr int TCQ_OFF_VS = TCQ_OFF_WP + TCQ_WP;                // [16][ldv] explicit V, multiple of 2 doubles (16-byte aligned)
 struct TcqShared {
-    double *Vs;      // [16][ldv]
-    double *Ts;      // [16][17]
-    double *Gs;      // [16][17]
-    double *red;     // [2][16 warps][16]
-    double *piv;     // [2][16]
-    double *taus;    // [16]
-    double *scr;     // [16 warps][TCQ_SCR]: W and W' per warp (also the per-warp 16 x 16 partial Gram tiles)
+    double *base;
+    __device__ __forceinline__ double *Ts() const { return base + TCQ_OFF_TS; }
+    __device__ __forceinline__ double *Gs() const { return base + TCQ_OFF_GS; }
+    __device__ __forceinline__ double *red() const { return base + TCQ_OFF_RED; }
+    __device__ __forceinline__ double *piv() const { return base + TCQ_OFF_PIV; }
+    __device__ __forceinline__ double *taus() const { return base + TCQ_OFF_TAU; }
+    __device__ __forceinline__ double *part() const { return base + TCQ_OFF_PART; }
+    __device__ __forceinline__ double *wp() const { return base + TCQ_OFF_WP; }
+    __device__ __forceinline__ double *Vs() const { return base + TCQ_OFF_VS; }
 };
 
 template<int RPT, int JJ>
@@ -433,10 +473,10 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
         for (int s = 0; s < NV; s++) part[s] = fma(x, p[JJ + s][i], part[s]);
     }
     TReduce<P, 16>::run(part, lane);
-    if ((lane & (32 / P - 1)) == 0) sh.red[(buf * TCQ_WARPS + warp) * TCQ_NB + lane / (32 / P)] = part[0];
+    if ((lane & (32 / P - 1)) == 0) sh.red()[(buf * TCQ_WARPS + warp) * TCQ_NB + lane / (32 / P)] = part[0];
     if (rr[0] == JJ) {                       // the owner of the pivot row publishes it
 #pragma unroll
-        for (int s = 0; s < NV; s++) sh.piv[buf * TCQ_NB + s] = p[JJ + s][0];
+        for (int s = 0; s < NV; s++) sh.piv()[buf * TCQ_NB + s] = p[JJ + s][0];
     }
     __syncthreads();
     // lane l < NV: total of value l (column JJ + l) and the pivot-row entry of that column
@@ -444,20 +484,37 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
     if (lane < NV) {
 #pragma unroll
         for (int w = 0; w < TCQ_WARPS; w += 2) {
-            tot += sh.red[(buf * TCQ_WARPS + w) * TCQ_NB + lane];
-            tot2 += sh.red[(buf * TCQ_WARPS + w + 1) * TCQ_NB + lane];
+            tot += sh.red()[(buf * TCQ_WARPS + w) * TCQ_NB + lane];
+            tot2 += sh.red()[(buf * TCQ_WARPS + w + 1) * TCQ_NB + lane];
         }
         tot += tot2;
-        pv = sh.piv[buf * TCQ_NB + lane];
+        pv = sh.piv()[buf * TCQ_NB + lane];
     }
     const double xnorm2 = __shfl_sync(0xffffffffu, tot, 0);
     const double alpha = __shfl_sync(0xffffffffu, pv, 0);
     double tau = 0.0, scale = 0.0, beta = alpha;
     if (xnorm2 != 0.0) {
-        const double nrm = sqrt(fma(alpha, alpha, xnorm2));
+        // dlarfg without the sqrt / divide slow paths (every warp evaluates this redundantly): rsqrt and rcp seeds
+        // plus Newton steps, each result corrected once more against its defining residual (< 1 ulp)
+        const double ss = fma(alpha, alpha, xnorm2);
+        double rn;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(ss));
+        const double hs = 0.5 * ss;
+        rn = fma(rn, fma(-hs, rn * rn, 0.5), rn);
+        rn = fma(rn, fma(-hs, rn * rn, 0.5), rn);
+        double nrm = ss * rn;
+        nrm = fma(fma(-nrm, nrm, ss), 0.5 * rn, nrm);
         beta = alpha >= 0.0 ? -nrm : nrm;
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+        const double rbeta = alpha >= 0.0 ? -rn : rn;
+        const double num = beta - alpha;
+        tau = num * rbeta;
+        tau = fma(fma(-tau, beta, num), rbeta, tau);
+        const double den = alpha - beta;
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+        y = fma(fma(-den, y, 1.0), y, y);
+        y = fma(fma(-den, y, 1.0), y, y);
+        scale = fma(fma(-den, y, 1.0), y, y);
     }
     const double coef = tau != 0.0 ? tau * fma(scale, tot, pv) : 0.0;      // lane l >= 1: tau * v^T a_(JJ+l)
     double v[RPT];
@@ -472,10 +529,275 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
 #pragma unroll
     for (int i = 0; i < RPT; i++) p[JJ][i] = rr[i] > JJ ? v[i] : (rr[i] == JJ ? beta : p[JJ][i]);
     if (warp == 0 && lane == 0) {
-        sh.taus[JJ] = tau;
+        sh.taus()[JJ] = tau;
         if (JJ < tau_ok_upto) tau_g[JJ] = tau;
     }
     if constexpr (JJ + 1 < TCQ_NB) tcq_panel_column<RPT, JJ + 1>(p, rr, sh, warp, lane, tau_g, tau_ok_upto);
+}
+
+// G = V^T V, T, and the trailing update A2 <- (I - V T^T V^T) A2 for one panel
+__device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t lda, int n, int j0, int mj, int ldv
+#ifdef GPUB_TCQ_PROFILE
+                                          , long long &tcq_t0
+#endif
+) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int mj16 = (mj + 15) & ~15;
+    const int ntrail = n - (j0 + TCQ_NB);
+    const unsigned vs_sh = (unsigned) __cvta_generic_to_shared(sh.Vs());
+    const unsigned v8off = (unsigned) (8 * ldv * 8);   // byte offset of V column c + 8
+    const int ncb = (ntrail + 7) / 8;
+    const int rg = warp >> 2, cq = warp & 3;
+    const int rpg = (((mj16 >> 2) + 7) & ~7);          // pass 1: rows per row group, multiple of 8
+    // L2 prefetch of this warp's pass-1 operand (its rows of its column blocks) for the chunk starting at cbs:
+    // issued a whole phase ahead, so pass 1 streams from L2 instead of waiting on DRAM. lane -> (column, 128-byte line)
+    auto prefetch_chunk = [&](int cbs) {
+        const int r0 = rg * rpg;
+#pragma unroll
+        for (int sl = 0; sl < TCQ_NSL; sl++) {
+            const int cb = cbs + cq + 4 * sl, col = j0 + TCQ_NB + 8 * cb + (lane & 7);
+            if (cb < ncb && col < n) {
+                const double *base = a_g + (size_t) j0 + (size_t) col * lda + r0;
+                for (int ln = lane >> 3; 16 * ln < rpg && r0 + 16 * ln < mj; ln += 4)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 16 * ln));
+            }
+        }
+    };
+    const int cb_last = ((ncb - 1) / (4 * TCQ_NSL)) * (4 * TCQ_NSL);
+    prefetch_chunk(cb_last);
+    // ---- G = V^T V: each warp one row range, upper three 8 x 8 tiles. Lane (g, q) takes rows r + 2q, r + 2q + 1
+    //      of a chunk of 8 (one LDS.128 per fragment pair; the k order inside a chunk is free) ----
+    {
+        const int kr = ((mj16 / 8 + TCQ_WARPS - 1) / TCQ_WARPS) * 8;
+        const int r0 = warp * kr, r1 = (r0 + kr) < mj16 ? (r0 + kr) : mj16;
+        double g00[2] = {0, 0}, g01[2] = {0, 0}, g11[2] = {0, 0};
+        unsigned va0 = vs_sh + (unsigned) ((g * ldv + 2 * q + r0) * 8);
+        for (int r = r0; r < r1; r += 8, va0 += 64) {
+            const double2 f0 = lds_f64x2(va0), f1 = lds_f64x2(va0 + v8off);
+            dmma884(g00[0], g00[1], f0.x, f0.x); dmma884(g00[0], g00[1], f0.y, f0.y);
+            dmma884(g01[0], g01[1], f0.x, f1.x); dmma884(g01[0], g01[1], f0.y, f1.y);
+            dmma884(g11[0], g11[1], f1.x, f1.x); dmma884(g11[0], g11[1], f1.y, f1.y);
+        }
+        double *gp = sh.part() + (size_t) warp * 256;
+        gp[g * 16 + 2 * q] = g00[0]; gp[g * 16 + 2 * q + 1] = g00[1];
+        gp[g * 16 + 8 + 2 * q] = g01[0]; gp[g * 16 + 8 + 2 * q + 1] = g01[1];
+        gp[(8 + g) * 16 + 8 + 2 * q] = g11[0]; gp[(8 + g) * 16 + 8 + 2 * q + 1] = g11[1];
+    }
+    __syncthreads();
+    if (tid < 256) {
+        const int i = tid >> 4, j = tid & 15;
+        if (i < j && !(i >= 8 && j < 8)) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < TCQ_WARPS; w++) acc += sh.part()[(size_t) w * 256 + tid];
+            sh.Gs()[i * 17 + j] = acc;
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && lane < TCQ_NB) {
+        double trow[TCQ_NB];
+#pragma unroll
+        for (int j = 0; j < TCQ_NB; j++) {
+            const double tj = sh.taus()[j];
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < j; k++)
+                if (k >= lane) acc = fma(trow[k], sh.Gs()[k * 17 + j], acc);
+            trow[j] = j == lane ? tj : (j > lane ? -tj * acc : 0.0);
+            sh.Ts()[lane * 17 + j] = trow[j];
+        }
+    }
+    __syncthreads();
+    TCQ_T(3);
+    // ---- trailing update: the 16 warps form a 4 (row groups) x 4 (column groups) grid; chunks of 16 column blocks ----
+    // A slot whose column block does not exist (or a lane whose column is >= n) reads a valid dummy column instead
+    // and never stores: the hot loops carry no load predicates. Every global access is 128-bit: the order of k inside
+    // a DMMA chunk and the assignment of tile rows are free, so lane (g, q) takes the row PAIRS r + 2q, r + 2q + 1
+    // (pass 1) and r + 2g, r + 2g + 1 (pass 2); a fragment load then moves 64 B (pass 1) or 128 B (pass 2) per
+    // cache line instead of 32 B, which is what keeps the L1 wavefront rate below the DMMA issue rate.
+    // chunks of 4 * TCQ_NSL column blocks, last chunk first: a chunk's pass 2 re-reads what its pass 1 just read while it is
+    // still in L2, and the columns of the next panel (chunk 0) are the most recently written when they are reloaded
+    for (int cb0 = cb_last; cb0 >= 0; cb0 -= 4 * TCQ_NSL) {
+        // pass 1: partial W = V^T A2 over the rows of this row group, for the (up to 4) column blocks cq, cq+4, ...
+        {
+            const int r0 = rg * rpg;
+            const int r1 = (r0 + rpg) < mj16 ? (r0 + rpg) : mj16;
+            const double *a2[TCQ_NSL];
+#pragma unroll
+            for (int sl = 0; sl < TCQ_NSL; sl++) {
+                const int cb = cb0 + cq + 4 * sl, c0 = j0 + TCQ_NB + 8 * cb;
+                const bool ok = cb < ncb && c0 + g < n;
+                a2[sl] = a_g + (size_t) j0 + (size_t) (ok ? c0 + g : j0) * lda + 2 * q + r0;
+            }
+            double acc[TCQ_NSL][2][2];
+#pragma unroll
+            for (int sl = 0; sl < TCQ_NSL; sl++) acc[sl][0][0] = acc[sl][0][1] = acc[sl][1][0] = acc[sl][1][1] = 0.0;
+            unsigned v0a = vs_sh + (unsigned) ((g * ldv + 2 * q + r0) * 8);
+            const int rlim = r1 < mj ? r1 : mj;
+            const int nfull = rlim > r0 ? (rlim - r0) >> 3 : 0;     // chunks of 8 rows that need no row guard
+            // software pipeline over chunks of 8 rows, TCQ_D1 - 1 chunks of loads in flight per warp (the pass is bound by
+            // bytes in flight x memory latency, not by the DMMA pipe, unless the prefetch distance is this deep)
+            double2 bq[TCQ_D1][TCQ_NSL];
+            auto ld = [&](double2 (&bb)[TCQ_NSL], int off_) {
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) bb[sl] = *reinterpret_cast<const double2 *>(a2[sl] + off_);
+            };
+            auto mm = [&](const double2 (&bb)[TCQ_NSL], unsigned va_) {
+                const double2 f0 = lds_f64x2(va_), f1 = lds_f64x2(va_ + v8off);
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    dmma884(acc[sl][0][0], acc[sl][0][1], f0.x, bb[sl].x);
+                    dmma884(acc[sl][1][0], acc[sl][1][1], f1.x, bb[sl].x);
+                }
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    dmma884(acc[sl][0][0], acc[sl][0][1], f0.y, bb[sl].y);
+                    dmma884(acc[sl][1][0], acc[sl][1][1], f1.y, bb[sl].y);
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < TCQ_D1 - 1; d++)
+                if (d < nfull) ld(bq[d], 8 * d);
+            int ch = 0;
+            for (; ch + TCQ_D1 <= nfull; ch += TCQ_D1) {
+#pragma unroll
+                for (int d = 0; d < TCQ_D1; d++) {
+                    if (ch + d + TCQ_D1 - 1 < nfull) ld(bq[(d + TCQ_D1 - 1) % TCQ_D1], 8 * (ch + d + TCQ_D1 - 1));
+                    mm(bq[d], v0a + 64 * (ch + d));
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < TCQ_D1 - 1; d++)
+                if (ch + d < nfull) mm(bq[d], v0a + 64 * (ch + d));
+            int off = 8 * nfull;
+            v0a += 64 * nfull;
+            for (int r = r0 + off; r < r1; r += 8, off += 8, v0a += 64) {   // guarded tail (V is zero beyond mj)
+                double2 bt[TCQ_NSL];
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    bt[sl].x = (r + 2 * q < mj) ? a2[sl][off] : 0.0;
+                    bt[sl].y = (r + 2 * q + 1 < mj) ? a2[sl][off + 1] : 0.0;
+                }
+                mm(bt, v0a);
+            }
+            // partial W of (row group, column block) -> part[rg][cbl][column][k]
+#pragma unroll
+            for (int sl = 0; sl < TCQ_NSL; sl++) {
+                double *pw = sh.part() + (size_t) (rg * 16 + cq + 4 * sl) * 128;
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    pw[(2 * q) * 16 + 8 * a + g] = acc[sl][a][0];
+                    pw[(2 * q + 1) * 16 + 8 * a + g] = acc[sl][a][1];
+                }
+            }
+        }
+        __syncthreads();
+        TCQ_T(4);
+        // W' = -T^T W for column block cbl = warp of this chunk: lane -> column c = lane & 7, rows i = (lane >> 3) + 4u
+        if (warp < 4 * TCQ_NSL && cb0 + warp < ncb) {
+            const int c = lane & 7;
+            double wc[TCQ_NB];
+            // (the 8 columns are 16 doubles apart: reading k in the rotated order (kk + 2c) & 15 spreads them over the banks)
+#pragma unroll
+            for (int kk = 0; kk < TCQ_NB; kk++) {
+                const double *pp = sh.part() + (size_t) warp * 128 + c * 16 + ((kk + 2 * c) & 15);
+                wc[kk] = (pp[0] + pp[16 * 128]) + (pp[32 * 128] + pp[48 * 128]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = (lane >> 3) + 4 * u;
+                double acc = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < TCQ_NB; kk++) {
+                    const int k = (kk + 2 * c) & 15;
+                    const double t = k <= i ? sh.Ts()[k * 17 + i] : 0.0;
+                    acc = fma(t, wc[kk], acc);
+                }
+                sh.wp()[(size_t) warp * (8 * TCQ_LDW) + c * TCQ_LDW + i] = -acc;
+            }
+        }
+        __syncthreads();
+        TCQ_T(5);
+        // pass 2: A2 blocks of 16 rows x 8 columns of this row group += V W', computed TRANSPOSED: D'(column, row) += W'^T V^T,
+        // so that lane (g, q) holds rows 2q, 2q + 1 of column g (one 128-bit access per tile; a quarter-warp touches two
+        // cache lines instead of four). A operand = W'^T (the same registers bw), B operand = V^T from shared memory.
+        if (cb0 > 0) prefetch_chunk(cb0 - 4 * TCQ_NSL);
+        {
+            const int nblk = mj16 >> 4;
+            const int bpg = (nblk + 3) >> 2;
+            const int b0 = rg * bpg;
+            const int b1 = (b0 + bpg) < nblk ? (b0 + bpg) : nblk;
+            double bw[TCQ_NSL][4];
+            double *cp[TCQ_NSL];      // rows 2q, 2q + 1 of column g of the slot's block
+            unsigned okmask = 0;      // bit sl: this lane's column of slot sl exists and is stored
+#pragma unroll
+            for (int sl = 0; sl < TCQ_NSL; sl++) {
+                const int cbl = cq + 4 * sl, cb = cb0 + cbl, c0 = j0 + TCQ_NB + 8 * cb;
+                const bool live = cb < ncb;
+                const bool ok = live && c0 + g < n;
+                okmask |= (ok ? 1u : 0u) << sl;
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) bw[sl][s4] = live ? sh.wp()[(size_t) cbl * (8 * TCQ_LDW) + g * TCQ_LDW + 4 * s4 + q] : 0.0;
+                cp[sl] = a_g + (size_t) j0 + (size_t) (ok ? c0 + g : j0) * lda + 2 * q + 16 * b0;
+            }
+            unsigned vaa = vs_sh + (unsigned) ((q * ldv + g + 16 * b0) * 8);
+            const unsigned s4off = (unsigned) (4 * ldv * 8);
+            const int bfull = (mj >> 4) < b1 ? (mj >> 4) : b1;       // blocks [b0, bfull) need no row guard
+            int off = 0, rb = b0;
+            for (; rb < bfull; rb++, off += 16, vaa += 128) {
+                double2 t1[TCQ_NSL], t2[TCQ_NSL];
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    t1[sl] = *reinterpret_cast<const double2 *>(cp[sl] + off);
+                    t2[sl] = *reinterpret_cast<const double2 *>(cp[sl] + off + 8);
+                }
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) {
+                    const double vb1 = lds_f64(vaa + s4 * s4off), vb2 = lds_f64(vaa + s4 * s4off + 64);
+#pragma unroll
+                    for (int sl = 0; sl < TCQ_NSL; sl++) {
+                        dmma884(t1[sl].x, t1[sl].y, bw[sl][s4], vb1);
+                        dmma884(t2[sl].x, t2[sl].y, bw[sl][s4], vb2);
+                    }
+                }
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    if (okmask & (1u << sl)) {
+                        *reinterpret_cast<double2 *>(cp[sl] + off) = t1[sl];
+                        *reinterpret_cast<double2 *>(cp[sl] + off + 8) = t2[sl];
+                    }
+                }
+            }
+            for (; rb < b1; rb++, off += 16, vaa += 128) {           // the partial last block (V is zero beyond mj)
+                const int rbase = 16 * rb + 2 * q;
+                double2 t1[TCQ_NSL], t2[TCQ_NSL];
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    t1[sl].x = rbase < mj ? cp[sl][off] : 0.0;          t1[sl].y = rbase + 1 < mj ? cp[sl][off + 1] : 0.0;
+                    t2[sl].x = rbase + 8 < mj ? cp[sl][off + 8] : 0.0;  t2[sl].y = rbase + 9 < mj ? cp[sl][off + 9] : 0.0;
+                }
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) {
+                    const double vb1 = lds_f64(vaa + s4 * s4off), vb2 = lds_f64(vaa + s4 * s4off + 64);
+#pragma unroll
+                    for (int sl = 0; sl < TCQ_NSL; sl++) {
+                        dmma884(t1[sl].x, t1[sl].y, bw[sl][s4], vb1);
+                        dmma884(t2[sl].x, t2[sl].y, bw[sl][s4], vb2);
+                    }
+                }
+#pragma unroll
+                for (int sl = 0; sl < TCQ_NSL; sl++) {
+                    if (okmask & (1u << sl)) {
+                        if (rbase < mj) cp[sl][off] = t1[sl].x;
+                        if (rbase + 1 < mj) cp[sl][off + 1] = t1[sl].y;
+                        if (rbase + 8 < mj) cp[sl][off + 8] = t2[sl].x;
+                        if (rbase + 9 < mj) cp[sl][off + 9] = t2[sl].y;
+                    }
+                }
+            }
+        }
+    }
 }
 
 template<int RPT>
@@ -483,13 +805,7 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
                                                               int ldv) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TcqShared sh;
-    sh.Vs = reinterpret_cast<double *>(smem_raw);
-    sh.Ts = sh.Vs + (size_t) TCQ_NB * ldv;
-    sh.Gs = sh.Ts + TCQ_NB * 17;
-    sh.red = sh.Gs + TCQ_NB * 17;
-    sh.piv = sh.red + 2 * TCQ_WARPS * TCQ_NB;
-    sh.taus = sh.piv + 2 * TCQ_NB;
-    sh.scr = sh.taus + TCQ_NB;
+    sh.base = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     const int kmax = n < m ? n : m;
@@ -497,10 +813,13 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         double *a_g = A + mat * sA;
         double *tau_g = tau + mat * sTau;
+#ifdef GPUB_TCQ_PROFILE
+        long long tcq_t0 = clock64();
+#endif
         for (int j0 = 0; j0 < kmax; j0 += TCQ_NB) {
             const int nb = (kmax - j0) < TCQ_NB ? (kmax - j0) : TCQ_NB;
             const int mj = m - j0;                       // rows of the panel
-            const int mj4 = (mj + 3) & ~3;
+            const int mj16 = (mj + 15) & ~15;             // V is zero-padded to a multiple of 16 rows
             // ---- panel into registers: thread owns panel rows tid, tid + 512, ... ----
             double p[TCQ_NB][RPT];
             int rr[RPT];
@@ -512,156 +831,32 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
                 for (int c = 0; c < TCQ_NB; c++) p[c][i] = (ok && c < nb) ? a_g[(size_t) (j0 + rr[i]) + (size_t) (j0 + c) * lda] : 0.0;
                 if (!ok) rr[i] = -1;                     // never "below the pivot"
             }
+            TCQ_T(0);
             tcq_panel_column<RPT, 0>(p, rr, sh, warp, lane, tau_g + j0, nb);
+            TCQ_T(1);
             // ---- factored panel back to global memory; explicit V (unit diagonal, zeros above) to shared memory ----
 #pragma unroll
             for (int i = 0; i < RPT; i++) {
                 const int r = tid + TCQ_THREADS * i;
-                if (r < mj4) {
+                if (r < mj16) {
 #pragma unroll
                     for (int c = 0; c < TCQ_NB; c++) {
                         if (r < mj && c < nb) a_g[(size_t) (j0 + r) + (size_t) (j0 + c) * lda] = p[c][i];
-                        sh.Vs[(size_t) c * ldv + r] = r < mj ? (r > c ? p[c][i] : (r == c ? 1.0 : 0.0)) : 0.0;
+                        sh.Vs()[(size_t) c * ldv + r] = r < mj ? (r > c ? p[c][i] : (r == c ? 1.0 : 0.0)) : 0.0;
                     }
                 }
             }
             const int ntrail = n - (j0 + TCQ_NB);
             if (ntrail <= 0) { __syncthreads(); continue; }
             __syncthreads();
-            // ---- G = V^T V: each warp one row range, upper three 8 x 8 tiles ----
-            {
-                const int kr = ((mj4 / 4 + TCQ_WARPS - 1) / TCQ_WARPS) * 4;
-                const int r0 = warp * kr, r1 = (r0 + kr) < mj4 ? (r0 + kr) : mj4;
-                double g00[2] = {0, 0}, g01[2] = {0, 0}, g11[2] = {0, 0};
-                const double *v0 = sh.Vs + (size_t) g * ldv + q, *v1 = sh.Vs + (size_t) (8 + g) * ldv + q;
-                for (int r = r0; r < r1; r += 4) {
-                    const double f0 = v0[r], f1 = v1[r];
-                    dmma884(g00[0], g00[1], f0, f0);
-                    dmma884(g01[0], g01[1], f0, f1);
-                    dmma884(g11[0], g11[1], f1, f1);
-                }
-                double *gp = sh.scr + (size_t) warp * TCQ_SCR;
-                gp[g * 16 + 2 * q] = g00[0]; gp[g * 16 + 2 * q + 1] = g00[1];
-                gp[g * 16 + 8 + 2 * q] = g01[0]; gp[g * 16 + 8 + 2 * q + 1] = g01[1];
-                gp[(8 + g) * 16 + 8 + 2 * q] = g11[0]; gp[(8 + g) * 16 + 8 + 2 * q + 1] = g11[1];
-            }
+            TCQ_T(2);
+            tcq_trailing(sh, a_g, lda, n, j0, mj, ldv
+#ifdef GPUB_TCQ_PROFILE
+                         , tcq_t0
+#endif
+            );
             __syncthreads();
-            if (tid < 256) {
-                const int i = tid >> 4, j = tid & 15;
-                if (i < j && !(i >= 8 && j < 8)) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int w = 0; w < TCQ_WARPS; w++) acc += sh.scr[(size_t) w * TCQ_SCR + tid];
-                    sh.Gs[i * 17 + j] = acc;
-                }
-            }
-            __syncthreads();
-            if (warp == 0 && lane < TCQ_NB) {
-                double trow[TCQ_NB];
-#pragma unroll
-                for (int j = 0; j < TCQ_NB; j++) {
-                    const double tj = sh.taus[j];
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < j; k++)
-                        if (k >= lane) acc = fma(trow[k], sh.Gs[k * 17 + j], acc);
-                    trow[j] = j == lane ? tj : (j > lane ? -tj * acc : 0.0);
-                    sh.Ts[lane * 17 + j] = trow[j];
-                }
-            }
-            __syncthreads();
-            // ---- trailing update, one warp per block of 8 columns ----
-            const int ncb = (ntrail + 7) / 8;
-            double *ws = sh.scr + (size_t) warp * TCQ_SCR, *wp = ws + 8 * TCQ_LDW;
-            for (int cb = warp; cb < ncb; cb += TCQ_WARPS) {
-                const int c0 = j0 + TCQ_NB + 8 * cb;
-                // pass 1: W = V^T A2 (16 x 8)
-                double w0[2] = {0, 0}, w1[2] = {0, 0}, x0[2] = {0, 0}, x1[2] = {0, 0};
-                {
-                    const bool col_ok = c0 + g < n;
-                    const double *a2 = a_g + (size_t) j0 + (size_t) (col_ok ? c0 + g : c0) * lda + q;
-                    const double *v0 = sh.Vs + (size_t) g * ldv + q, *v1 = sh.Vs + (size_t) (8 + g) * ldv + q;
-                    int r = 0;
-                    for (; r + 16 <= mj; r += 16) {
-                        double bfr[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) bfr[u] = col_ok ? a2[r + 4 * u] : 0.0;
-#pragma unroll
-                        for (int u = 0; u < 4; u += 2) {
-                            dmma884(w0[0], w0[1], v0[r + 4 * u], bfr[u]);
-                            dmma884(w1[0], w1[1], v1[r + 4 * u], bfr[u]);
-                            dmma884(x0[0], x0[1], v0[r + 4 * u + 4], bfr[u + 1]);
-                            dmma884(x1[0], x1[1], v1[r + 4 * u + 4], bfr[u + 1]);
-                        }
-                    }
-                    for (; r < mj4; r += 4) {
-                        const double bf = (col_ok && r + q < mj) ? a2[r] : 0.0;
-                        dmma884(w0[0], w0[1], v0[r], bf);
-                        dmma884(w1[0], w1[1], v1[r], bf);
-                    }
-                    w0[0] += x0[0]; w0[1] += x0[1]; w1[0] += x1[0]; w1[1] += x1[1];
-                }
-                // W (accumulator layout: rows g / 8 + g, columns 2q, 2q + 1) -> ws[column][k]
-                __syncwarp();
-                ws[(2 * q) * TCQ_LDW + g] = w0[0]; ws[(2 * q + 1) * TCQ_LDW + g] = w0[1];
-                ws[(2 * q) * TCQ_LDW + 8 + g] = w1[0]; ws[(2 * q + 1) * TCQ_LDW + 8 + g] = w1[1];
-                __syncwarp();
-                // W' = -T^T W: lane -> column c = lane & 7, rows i = (lane >> 3) + 4u
-                {
-                    const int c = lane & 7;
-                    double wc[TCQ_NB];
-#pragma unroll
-                    for (int k = 0; k < TCQ_NB; k++) wc[k] = ws[c * TCQ_LDW + k];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = (lane >> 3) + 4 * u;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < TCQ_NB; k++)
-                            if (k <= i) acc = fma(sh.Ts[k * 17 + i], wc[k], acc);
-                        wp[c * TCQ_LDW + i] = -acc;
-                    }
-                }
-                __syncwarp();
-                // pass 2: A2 tile += V W'
-                double bw[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) bw[s4] = wp[g * TCQ_LDW + 4 * s4 + q];
-                const bool c_ok0 = c0 + 2 * q < n, c_ok1 = c0 + 2 * q + 1 < n;
-                double *t0 = a_g + (size_t) j0 + (size_t) (c0 + 2 * q) * lda + g;
-                double *t1 = t0 + lda;
-                const double *va = sh.Vs + (size_t) q * ldv + g;
-                const int ntile = (mj + 7) / 8;
-                int rt = 0;
-                for (; rt + 4 <= ntile && 8 * (rt + 4) <= mj; rt += 4) {
-                    double c[4][2];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        c[u][0] = c_ok0 ? t0[8 * (rt + u)] : 0.0;
-                        c[u][1] = c_ok1 ? t1[8 * (rt + u)] : 0.0;
-                    }
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++)
-#pragma unroll
-                        for (int u = 0; u < 4; u++) dmma884(c[u][0], c[u][1], va[(size_t) (4 * s4) * ldv + 8 * (rt + u)], bw[s4]);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (c_ok0) t0[8 * (rt + u)] = c[u][0];
-                        if (c_ok1) t1[8 * (rt + u)] = c[u][1];
-                    }
-                }
-                for (; rt < ntile; rt++) {
-                    const bool r_ok = 8 * rt + g < mj;
-                    double c[2];
-                    c[0] = (r_ok && c_ok0) ? t0[8 * rt] : 0.0;
-                    c[1] = (r_ok && c_ok1) ? t1[8 * rt] : 0.0;
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) dmma884(c[0], c[1], r_ok ? va[(size_t) (4 * s4) * ldv + 8 * rt] : 0.0, bw[s4]);
-                    if (r_ok && c_ok0) t0[8 * rt] = c[0];
-                    if (r_ok && c_ok1) t1[8 * rt] = c[1];
-                }
-            }
-            __syncthreads();
+            TCQ_T(6);
         }
     }
 }
@@ -671,9 +866,10 @@ bool try_geqrf_tc(gpub_ctx_t, cudaStream_t, size_t, size_t, T *, size_t, size_t,
 template<>
 bool try_geqrf_tc<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sTau,
                           size_t batch, int *err) {
-    if (m > 1024 || m < 64 || n < 16) return false;
-    const size_t ldv = (m + 15) / 16 * 16 + 4;
-    const size_t smem = (TCQ_NB * ldv + 2 * TCQ_NB * 17 + 2 * TCQ_WARPS * TCQ_NB + 2 * TCQ_NB + TCQ_NB + (size_t) TCQ_WARPS * TCQ_SCR) * sizeof(double);
+    if (m > 1024 || m < 64 || n < 16 || (n & 1)) return false;   // odd n: a lane's two tile columns would straddle the edge
+    if ((lda & 1) || (sA & 1) || (((uintptr_t) A) & 15u)) return false;   // 128-bit accesses to column pairs of rows
+    const size_t ldv = (m + 15) / 16 * 16 + 8;   // = 8 (mod 16): the 128-bit fragment loads of pass 1 are bank-conflict free
+    const size_t smem = ((size_t) TCQ_OFF_VS + TCQ_NB * ldv) * sizeof(double);
     if (smem > (size_t) ctx->max_smem_optin) return false;
     const unsigned grid = (unsigned) (batch < (size_t) ctx->sm_count ? batch : (size_t) ctx->sm_count);
     cudaError_t e;
@@ -1002,6 +1198,15 @@ int gels_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda,
 } // namespace
 
 extern "C" {
+
+#ifdef GPUB_TCQ_PROFILE
+int gpub_debug_tcq_profile(unsigned long long *out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_tcq_prof, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tcq_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int gpub_geqrf_batched_f64(gpub_ctx_t c, int s, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sT, size_t b) { return geqrf_batched<double>(c, s, m, n, A, lda, sA, tau, sT, b); }
 int gpub_geqrf_batched_f32(gpub_ctx_t c, int s, size_t m, size_t n, float *A, size_t lda, size_t sA, float *tau, size_t sT, size_t b) { return geqrf_batched<float>(c, s, m, n, A, lda, sA, tau, sT, b); }

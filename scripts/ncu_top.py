@@ -27,3 +27,11 @@ for i in sorted(order):
     r = rows[i]
     st = sorted(((int(r[ci[s]] or 0), s[6:]) for s in stall_cols), reverse=True)[:3]
     print(f"{i:5d} {int(r[ci['# Samples']])*100/tot:5.1f}%  exec={r[ci['Instructions Executed']]:>9s}  {r[ci['Source']].strip()[:70]:70s} " + " ".join(f"{n}:{c}" for c, n in st if c))
+if len(sys.argv) > 5:
+    # cumulative sample share per block of K instructions
+    K = int(sys.argv[5]); acc = collections.Counter(); st = collections.defaultdict(collections.Counter)
+    for i, r in enumerate(rows):
+        acc[i // K] += int(r[ci["# Samples"]])
+        for s in stall_cols: st[i // K][s[6:]] += int(r[ci[s]] or 0)
+    for b_ in sorted(acc):
+        print(f"[{b_*K:5d}-{b_*K+K-1:5d}] {acc[b_]*100/tot:5.1f}%  " + " ".join(f"{n}:{c*100//max(acc[b_],1)}%" for n, c in st[b_].most_common(4)))
