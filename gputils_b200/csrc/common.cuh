@@ -18,6 +18,8 @@ struct gpub_stream_slot {
     void *d_scratch = nullptr;         // GPUB_SCRATCH_BYTES of device scratch (reduction partials)
     unsigned int *d_counter = nullptr; // "last block" ticket, always left at zero
     void *h_result = nullptr;          // pinned + mapped host buffer the final block writes into
+    void *d_big = nullptr;             // grow-only device scratch (alias copies of small operands), see gpub_slot_big
+    size_t big_bytes = 0;
 };
 
 struct gpub_ctx {
@@ -53,6 +55,11 @@ struct gpub_device_guard {
 // Resolves (ctx, sidx) to a usable slot, creating streams lazily. Returns nullptr on bad arguments.
 gpub_stream_slot *gpub_slot(gpub_ctx_t ctx, int sidx, int *err);
 
+// Context-owned, grow-only scratch of the slot (at least `bytes`, 256-byte aligned), or nullptr when bytes exceeds
+// GPUB_BIG_MAX_BYTES (callers then fall back to a stream-ordered allocation). Growing synchronises the slot's stream.
+#define GPUB_BIG_MAX_BYTES (256ull << 20)
+void *gpub_slot_big(gpub_stream_slot *slot, size_t bytes);
+
 #define GPUB_ENTER(ctx, sidx)                              \
     if (!(ctx)) return GPUB_EINVAL;                        \
     gpub_device_guard gpub_guard_((ctx)->device);          \
@@ -80,5 +87,25 @@ __host__ __device__ __forceinline__ double gpub_u01(uint64_t seed, uint64_t i) {
     uint64_t h = gpub_mix64(seed ^ gpub_mix64(i));
     return (double) (h >> 11) * (1.0 / 9007199254740992.0);
 }
+
+// v[0..P-1] per lane -> v[0] = sum over the 32 lanes of value number lane / (32 / P)   (P a power of two <= 32)
+template<typename T, int P, int O>
+struct TReduce {
+    static __device__ __forceinline__ void run(T *v, int lane) {
+        if constexpr (P > 1) {
+            constexpr int H = P / 2;
+            const bool up = (lane & O) != 0;
+#pragma unroll
+            for (int k = 0; k < H; k++) {
+                const T keep = up ? v[H + k] : v[k];
+                const T send = up ? v[k] : v[H + k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+        }
+        if constexpr (O > 1) TReduce<T, (P > 1 ? P / 2 : 1), O / 2>::run(v, lane);
+    }
+};
 
 static inline size_t gpub_ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }

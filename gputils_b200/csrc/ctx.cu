@@ -48,6 +48,26 @@ gpub_stream_slot *gpub_slot(gpub_ctx_t ctx, int sidx, int *err) {
     return &s;
 }
 
+void *gpub_slot_big(gpub_stream_slot *slot, size_t bytes) {
+    if (!slot || bytes > GPUB_BIG_MAX_BYTES) return nullptr;
+    if (bytes <= slot->big_bytes) return slot->d_big;
+    if (slot->d_big) {
+        if (cudaStreamSynchronize(slot->stream) != cudaSuccess) return nullptr;
+        cudaFree(slot->d_big);
+        slot->d_big = nullptr;
+        slot->big_bytes = 0;
+    }
+    size_t want = bytes + bytes / 2;
+    want = (want + 255) & ~(size_t) 255;
+    if (want > GPUB_BIG_MAX_BYTES) want = GPUB_BIG_MAX_BYTES;
+    if (cudaMalloc(&slot->d_big, want) != cudaSuccess) {
+        slot->d_big = nullptr;
+        return nullptr;
+    }
+    slot->big_bytes = want;
+    return slot->d_big;
+}
+
 extern "C" {
 
 const char *gpub_version(void) { return "gputils_b200 0.1 (sm_100a)"; }
@@ -139,6 +159,7 @@ int gpub_ctx_release(gpub_ctx_t ctx) {
         if (s.d_scratch) keep(cudaFree(s.d_scratch));
         if (s.d_counter) keep(cudaFree(s.d_counter));
         if (s.h_result) keep(cudaFreeHost(s.h_result));
+        if (s.d_big) keep(cudaFree(s.d_big));
         if (s.stream && s.owned) keep(cudaStreamDestroy(s.stream));
         s = gpub_stream_slot();   // recreated lazily if the slot is used again
     }

@@ -356,13 +356,16 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// TRB: the second operand is given transposed (B = Bt^T with Bt n x k column-major, ldb its leading dimension): the
+// panel then lands as [kk][col] like A's and its fragments are read with A's conflict-free pattern (P = N N^T).
+template<bool TRB>
 __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
                                                     size_t tiles_n, size_t batch) {
     // As[buf][kk][row] (A panel, 16 x 64), Bs[buf][col][kk] (B panel stored k-contiguous per column)
     __shared__ __align__(16) double As[2][DK][DLD];
-    __shared__ __align__(16) double Bs[2][64][DK + 4];
+    __shared__ __align__(16) double Bs[2][TRB ? DK : 64][TRB ? DLD : DK + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32; // warp origin inside the tile
     const int g = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
         const size_t b = t / tiles, r = t - b * tiles;
         const size_t row0 = (r % tiles_m) * 64, col0 = (r / tiles_m) * 64;
         const double *a = A + b * sA + row0;
-        const double *bb = B + b * sB + col0 * ldb;
+        const double *bb = B + b * sB + (TRB ? col0 : col0 * ldb);
         double acc[2][4][2];
 #pragma unroll
         for (int i = 0; i < 2; i++)
@@ -390,8 +393,13 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
 #pragma unroll
             for (int l = 0; l < 2; l++) {
                 int e = threadIdx.x + l * 256;
-                int kk = (e & 7) * 2, cc = e >> 3;
-                cp_async16(&Bs[buf][cc][kk], bb + (k0 + kk) + (size_t) cc * ldb);
+                if (TRB) {
+                    int cc = (e & 31) * 2, kk = e >> 5;
+                    cp_async16(&Bs[buf][kk][cc], bb + cc + (k0 + kk) * ldb);
+                } else {
+                    int kk = (e & 7) * 2, cc = e >> 3;
+                    cp_async16(&Bs[buf][cc][kk], bb + (k0 + kk) + (size_t) cc * ldb);
+                }
             }
             cp_async_commit();
         };
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
 #pragma unroll
                 for (int i = 0; i < 2; i++) af[i] = As[buf][k4 + q][wr + 8 * i + g]; // A(row g, k q)
 #pragma unroll
-                for (int j = 0; j < 4; j++) bf[j] = Bs[buf][wc + 8 * j + g][k4 + q]; // B(k q, col g)
+                for (int j = 0; j < 4; j++) bf[j] = TRB ? Bs[buf][k4 + q][wc + 8 * j + g] : Bs[buf][wc + 8 * j + g][k4 + q]; // B(k q, col g)
 #pragma unroll
                 for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -733,6 +741,59 @@ bool try_sgemm32<float>(gpub_ctx_t ctx, cudaStream_t stream, float alpha, const 
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// n == 1 (batched matrix-vector, Nullspace::project and the example's d_A * d_b): k_gemv<T>
+// HBM-bound: A is read exactly once. A CTA takes 64 rows of one matrix; its 256 threads are 64 rows x 4 interleaved
+// k-slices, so one pass over a column touches 512 contiguous bytes per slice and four columns are in flight per
+// CTA (more with the unrolled loop). x is staged in shared memory in chunks, the four slice sums are combined
+// through shared memory in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int GEMV_ROWS = 64, GEMV_KS = 4, GEMV_XCHUNK = 2048;
+
+template<typename T>
+__global__ void __launch_bounds__(GEMV_ROWS * GEMV_KS) k_gemv(size_t m, size_t k, T alpha, const T *__restrict__ A, size_t lda, size_t sA,
+                                                               const T *__restrict__ x, size_t sX, T beta, T *y, size_t sY, size_t row_blocks,
+                                                               size_t batch) {
+    __shared__ T xs[GEMV_XCHUNK];
+    __shared__ T part[GEMV_KS][GEMV_ROWS];
+    const int r = threadIdx.x % GEMV_ROWS, ks = threadIdx.x / GEMV_ROWS;
+    for (size_t t = blockIdx.x; t < batch * row_blocks; t += gridDim.x) {
+        const size_t mat = t / row_blocks, rb = t - mat * row_blocks;
+        const size_t row = rb * GEMV_ROWS + r;
+        const bool row_ok = row < m;
+        const T *a = A + mat * sA + (row_ok ? row : 0);
+        const T *xg = x + mat * sX;
+        T acc0 = 0, acc1 = 0;
+        for (size_t k0 = 0; k0 < k; k0 += GEMV_XCHUNK) {
+            const size_t kc = (k - k0) < (size_t) GEMV_XCHUNK ? (k - k0) : (size_t) GEMV_XCHUNK;
+            __syncthreads();
+            for (size_t j = threadIdx.x; j < kc; j += blockDim.x) xs[j] = xg[k0 + j];
+            __syncthreads();
+            const T *ac = a + (k0 + ks) * lda;
+            size_t j = ks;
+#pragma unroll 1
+            for (; j + 7 * GEMV_KS < kc; j += 8 * GEMV_KS, ac += 8 * GEMV_KS * lda) {
+                T v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = ac[(size_t) u * GEMV_KS * lda];
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    acc0 = fma(v[u], xs[j + u * GEMV_KS], acc0);
+                    acc1 = fma(v[u + 1], xs[j + (u + 1) * GEMV_KS], acc1);
+                }
+            }
+            for (; j < kc; j += GEMV_KS, ac += GEMV_KS * lda) acc0 = fma(*ac, xs[j], acc0);
+        }
+        part[ks][r] = acc0 + acc1;
+        __syncthreads();
+        if (ks == 0 && row_ok) {
+            const T sum = (part[0][r] + part[1][r]) + (part[2][r] + part[3][r]);
+            T *yp = y + mat * sY + row;
+            *yp = beta == T(0) ? alpha * sum : alpha * sum + beta * (*yp);
+        }
+    }
+}
+
 template<typename T> struct UseDmma { static constexpr bool value = false; };
 template<> struct UseDmma<double> { static constexpr bool value = true; };
 
@@ -807,16 +868,29 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
     const size_t spanB = ((batch - 1) * sB + (n - 1) * ldb + k) * sizeof(T);
     const size_t spanA = ((batch - 1) * sA + (k ? (k - 1) : 0) * lda + m) * sizeof(T);
     const size_t spanC = ((batch - 1) * sC + (n - 1) * ldc + m) * sizeof(T);
+    // scratch: the context's grow-only buffer when both copies fit (no allocation on the hot path), else stream-ordered
     T *tmpA = nullptr, *tmpB = nullptr;
-    if (k > 0 && ranges_overlap(C, spanC, B, spanB)) {
-        GPUB_CUDA(cudaMallocAsync((void **) &tmpB, spanB, stream));
-        GPUB_CUDA(cudaMemcpyAsync(tmpB, B, spanB, cudaMemcpyDeviceToDevice, stream));
-        B = tmpB;
-    }
-    if (k > 0 && ranges_overlap(C, spanC, A, spanA)) {
-        GPUB_CUDA(cudaMallocAsync((void **) &tmpA, spanA, stream));
-        GPUB_CUDA(cudaMemcpyAsync(tmpA, A, spanA, cudaMemcpyDeviceToDevice, stream));
-        A = tmpA;
+    const bool aliasB = k > 0 && ranges_overlap(C, spanC, B, spanB), aliasA = k > 0 && ranges_overlap(C, spanC, A, spanA);
+    bool pooled = false;
+    if (aliasA || aliasB) {
+        const size_t needB = aliasB ? (spanB + 255) & ~(size_t) 255 : 0, needA = aliasA ? spanA : 0;
+        char *big = (char *) gpub_slot_big(slot, needA + needB);
+        if (big) {
+            pooled = true;
+            if (aliasB) tmpB = (T *) big;
+            if (aliasA) tmpA = (T *) (big + needB);
+        } else {
+            if (aliasB) GPUB_CUDA(cudaMallocAsync((void **) &tmpB, spanB, stream));
+            if (aliasA) GPUB_CUDA(cudaMallocAsync((void **) &tmpA, spanA, stream));
+        }
+        if (aliasB) {
+            GPUB_CUDA(cudaMemcpyAsync(tmpB, B, spanB, cudaMemcpyDeviceToDevice, stream));
+            B = tmpB;
+        }
+        if (aliasA) {
+            GPUB_CUDA(cudaMemcpyAsync(tmpA, A, spanA, cudaMemcpyDeviceToDevice, stream));
+            A = tmpA;
+        }
     }
 
     const size_t tm = gpub_ceil_div(m, 64), tn = gpub_ceil_div(n, 64);
@@ -824,11 +898,18 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
     const size_t cap = (size_t) ctx->sm_count * 8;
     const unsigned grid = (unsigned) (total < cap ? total : cap);
     bool done = false;
-    if (UseDmma<T>::value) {
+    if (n == 1 && k > 0) {
+        const size_t row_blocks = gpub_ceil_div(m, (size_t) GEMV_ROWS), items = row_blocks * batch;
+        const size_t vcap = (size_t) ctx->sm_count * 16;
+        k_gemv<T><<<(unsigned) (items < vcap ? items : vcap), GEMV_ROWS * GEMV_KS, 0, stream>>>(m, k, alpha, A, lda, sA, B, sB, beta, C, sC,
+                                                                                                  row_blocks, batch);
+        done = true;
+    }
+    if (!done && UseDmma<T>::value) {
         const bool ok = (m % 64 == 0) && (n % 64 == 0) && (k % DK == 0) && k >= DK && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         ((((uintptr_t) A) | ((uintptr_t) B)) % 16 == 0) && (sA % 2 == 0) && (sB % 2 == 0);
         if (ok) {
-            k_gemm_dmma<<<grid, 256, 0, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+            k_gemm_dmma<false><<<grid, 256, 0, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
                                                   ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
             done = true;
         }
@@ -837,8 +918,8 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
     if (!done)
         k_gemm_tiled<T><<<grid, 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
     GPUB_LAUNCH_CHECK();
-    if (tmpA) GPUB_CUDA(cudaFreeAsync(tmpA, stream));
-    if (tmpB) GPUB_CUDA(cudaFreeAsync(tmpB, stream));
+    if (!pooled && tmpA) GPUB_CUDA(cudaFreeAsync(tmpA, stream));
+    if (!pooled && tmpB) GPUB_CUDA(cudaFreeAsync(tmpB, stream));
     return GPUB_OK;
 }
 
@@ -855,6 +936,15 @@ __global__ void k_aat(size_t n, const T *__restrict__ N, size_t sN, T *__restric
             P[b * sP + e] = acc;
         }
     }
+}
+
+template<typename T> bool try_aat_dmma(gpub_ctx_t, cudaStream_t, size_t, const T *, size_t, T *, size_t, size_t) { return false; }
+template<>
+bool try_aat_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *N, size_t sN, double *P, size_t sP, size_t batch) {
+    if (n % 64 != 0 || (sN & 1) || (((uintptr_t) N) & 15u)) return false;
+    const size_t tm = n / 64, total = tm * tm * batch, cap = (size_t) ctx->sm_count * 8;
+    k_gemm_dmma<true><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
+    return true;
 }
 
 } // namespace
@@ -878,6 +968,7 @@ int gpub_gemm_batched_f32(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k
         if (n == 0 || batch == 0) return GPUB_OK;                                                                    \
         if (!N || !P) return GPUB_EINVAL;                                                                            \
         GPUB_ENTER(ctx, sidx);                                                                                       \
+        if (try_aat_dmma<T>(ctx, stream, n, N, sN, P, sP, batch)) { GPUB_LAUNCH_CHECK(); return GPUB_OK; }           \
         unsigned gx = (unsigned) (gpub_ceil_div(n * n, 256) < 4096 ? gpub_ceil_div(n * n, 256) : 4096);              \
         unsigned gy = (unsigned) (batch < 65535 ? batch : 65535);                                                    \
         k_aat<T><<<dim3(gx, gy), 256, 0, stream>>>(n, N, sN, P, sP, batch);                                          \

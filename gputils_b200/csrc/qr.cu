@@ -413,26 +413,6 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     return v;
 }
 
-// v[0..P-1] per lane -> v[0] = sum over the 32 lanes of value number lane / (32 / P)   (P a power of two <= 32)
-template<int P, int O>
-struct TReduce {
-    static __device__ __forceinline__ void run(double *v, int lane) {
-        if constexpr (P > 1) {
-            constexpr int H = P / 2;
-            const bool up = (lane & O) != 0;
-#pragma unroll
-            for (int k = 0; k < H; k++) {
-                const double keep = up ? v[H + k] : v[k];
-                const double send = up ? v[k] : v[H + k];
-                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, O);
-            }
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
-        }
-        if constexpr (O > 1) TReduce<(P > 1 ? P / 2 : 1), O / 2>::run(v, lane);
-    }
-};
-
 __host__ __device__ constexpr int tcq_pow2ceil(int x) { return x <= 1 ? 1 : (x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : 16))); }
 
 // shared-memory layout: fixed-size regions first, so every address is base + compile-time offset (one live pointer)
@@ -472,7 +452,7 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
 #pragma unroll
         for (int s = 0; s < NV; s++) part[s] = fma(x, p[JJ + s][i], part[s]);
     }
-    TReduce<P, 16>::run(part, lane);
+    TReduce<double, P, 16>::run(part, lane);
     if ((lane & (32 / P - 1)) == 0) sh.red()[(buf * TCQ_WARPS + warp) * TCQ_NB + lane / (32 / P)] = part[0];
     if (rr[0] == JJ) {                       // the owner of the pivot row publishes it
 #pragma unroll

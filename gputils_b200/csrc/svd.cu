@@ -71,10 +71,35 @@ __global__ void k_init_u(int m, int n, const T *__restrict__ Ur, size_t sUr, T *
 // an orthogonal matrix, which Nullspace relies on.
 // ------------------------------------------------------------------------------------------
 constexpr int JT = 512; // threads per CTA
+constexpr int JP = 4;   // pairs a warp rotates at once
 
 template<typename T> struct JacobiEps;
-template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; };
-template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; };
+template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; };
+template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; static constexpr float big = 1e15f; };
+
+// reciprocal square root / reciprocal from the MUFU seed plus Newton steps (~1 ulp, no slow-path call)
+template<typename T> __device__ __forceinline__ T jac_rsqrt(T x);
+template<> __device__ __forceinline__ double jac_rsqrt<double>(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    y = fma(y, fma(-h, y * y, 0.5), y);
+    return y;
+}
+template<> __device__ __forceinline__ float jac_rsqrt<float>(float x) {
+    const float y = rsqrtf(x);
+    return fmaf(0.5f * y, fmaf(-x * y, y, 1.0f), y);
+}
+template<typename T> __device__ __forceinline__ T jac_rcp(T x);
+template<> __device__ __forceinline__ double jac_rcp<double>(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    y = fma(fma(-x, y, 1.0), y, y);
+    return fma(fma(-x, y, 1.0), y, y);
+}
+template<> __device__ __forceinline__ float jac_rcp<float>(float x) { return __frcp_rn(x); }
 
 template<typename T>
 __device__ __forceinline__ T jwarp_sum(T v) {
@@ -83,7 +108,8 @@ __device__ __forceinline__ T jwarp_sum(T v) {
     return v;
 }
 
-template<typename T>
+// JE: rows per lane (n <= 32 * JE)
+template<typename T, int JE>
 __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A, size_t lda, size_t sA, T *S, size_t sS, T *Vt, size_t ldvt,
                                                   size_t sVt, T *Ur, size_t sUr, int want_u, int *info, size_t batch, int ldx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,6 +124,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
     constexpr int NW = JT / 32;
     const int npad = n + (n & 1);                       // circle method needs an even count; index n is a bye
     const T tol = (T) JacobiEps<T>::v * sqrt((T) n);
+    const T tol2 = tol * tol;
 
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         const T *a_g = A + mat * sA;
@@ -113,45 +140,91 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
             if (tid == 0) s_rot = 0;
             __syncthreads();
             for (int round = 0; round < npad - 1; round++) {
-                for (int i = warp; i < npad / 2; i += NW) {
-                    int p, q;
-                    if (i == 0) {
-                        p = npad - 1;
-                        q = round;
-                    } else {
-                        p = (round + i) % (npad - 1);
-                        q = (round - i + (npad - 1)) % (npad - 1);
-                    }
-                    if (p >= n || q >= n) continue;      // bye
-                    if (p > q) { int t = p; p = q; q = t; }
-                    T *xp = X + (size_t) p * ldx, *xq = X + (size_t) q * ldx;
-                    T aa = 0, bb = 0, cc = 0;
-                    for (int r = lane; r < n; r += 32) {
-                        const T u = xp[r], v = xq[r];
-                        aa = fma(u, u, aa);
-                        bb = fma(v, v, bb);
-                        cc = fma(u, v, cc);
-                    }
-                    aa = jwarp_sum(aa); bb = jwarp_sum(bb); cc = jwarp_sum(cc);
-                    if (fabs(cc) > tol * sqrt(aa * bb) && cc != T(0)) {
-                        const T zeta = (bb - aa) / (T(2) * cc);
-                        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-                        const T cs = T(1) / sqrt(T(1) + t * t), sn = cs * t;
-                        for (int r = lane; r < n; r += 32) {
-                            const T u = xp[r], v = xq[r];
-                            xp[r] = cs * u - sn * v;
-                            xq[r] = sn * u + cs * v;
+                // a warp works on (up to) JP disjoint pairs of the round at once: their columns are held in registers, the 3 * JP
+                // dot products go through one transpose-reduce butterfly, and the JP rotations are independent instruction
+                // streams -- the dependent chain (reduce -> rotation -> update) of one pair no longer idles the warp
+                for (int base = warp; base < npad / 2; base += JP * NW) {
+                    int pp[JP], qq[JP];
+                    unsigned vmask = 0;
+                    T cu[JP][JE], cv[JP][JE];
+                    T red[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) red[e] = T(0);
+#pragma unroll
+                    for (int u = 0; u < JP; u++) {
+                        const int i = base + u * NW;
+                        int p = -1, q = -1;
+                        if (i < npad / 2) {
+                            if (i == 0) { p = npad - 1; q = round; }
+                            else { p = (round + i) % (npad - 1); q = (round - i + (npad - 1)) % (npad - 1); }
+                            if (p >= n || q >= n) { p = -1; q = -1; }      // bye
+                            else if (p > q) { const int t = p; p = q; q = t; }
                         }
-                        if (want_u) {
-                            T *jp = J + (size_t) p * n, *jq = J + (size_t) q * n;
-                            for (int r = lane; r < n; r += 32) {
-                                const T u = jp[r], v = jq[r];
-                                jp[r] = cs * u - sn * v;
-                                jq[r] = sn * u + cs * v;
+                        pp[u] = p; qq[u] = q;
+                        vmask |= (p >= 0 ? 1u : 0u) << u;
+                        T aa = 0, bb = 0, cc = 0;
+#pragma unroll
+                        for (int e = 0; e < JE; e++) {
+                            const int r = lane + 32 * e;
+                            const bool ok = p >= 0 && r < n;
+                            cu[u][e] = ok ? X[(size_t) p * ldx + r] : T(0);
+                            cv[u][e] = ok ? X[(size_t) q * ldx + r] : T(0);
+                            aa = fma(cu[u][e], cu[u][e], aa);
+                            bb = fma(cv[u][e], cv[u][e], bb);
+                            cc = fma(cu[u][e], cv[u][e], cc);
+                        }
+                        red[3 * u] = aa; red[3 * u + 1] = bb; red[3 * u + 2] = cc;
+                    }
+                    TReduce<T, 16, 16>::run(red, lane);          // lane l now holds the total of value l >> 1
+                    const T tot = red[0];
+                    // lane u (< JP) gathers the three sums of pair u and computes ITS rotation: the parameters of the JP pairs
+                    // cost one instruction stream instead of JP (rsqrt / rcp seeds + Newton steps, no sqrt / divide slow paths)
+                    const int src = 6 * (lane & 3);
+                    const T aa = __shfl_sync(0xffffffffu, tot, src), bb = __shfl_sync(0xffffffffu, tot, src + 2),
+                            cc = __shfl_sync(0xffffffffu, tot, src + 4);
+                    T cs = T(1), sn = T(0);
+                    bool rot = false;
+                    if (((vmask >> (lane & 3)) & 1u) && cc != T(0) && cc * cc > tol2 * (aa * bb)) {
+                        const T zeta = (bb - aa) * jac_rcp<T>(T(2) * cc);
+                        const T az = fabs(zeta);
+                        T t;
+                        if (az > JacobiEps<T>::big) {
+                            t = jac_rcp<T>(T(2) * az);
+                        } else {
+                            const T w = fma(zeta, zeta, T(1));
+                            t = jac_rcp<T>(az + w * jac_rsqrt<T>(w));
+                        }
+                        t = zeta >= T(0) ? t : -t;
+                        cs = jac_rsqrt<T>(fma(t, t, T(1)));
+                        sn = cs * t;
+                        rot = true;
+                    }
+                    const unsigned rmask = __ballot_sync(0xffffffffu, rot) & ((1u << JP) - 1u);
+#pragma unroll
+                    for (int u = 0; u < JP; u++) {
+                        const T cu_ = __shfl_sync(0xffffffffu, cs, u), su_ = __shfl_sync(0xffffffffu, sn, u);
+                        if ((rmask >> u) & 1u) {
+                            T *xp = X + (size_t) pp[u] * ldx, *xq = X + (size_t) qq[u] * ldx;
+#pragma unroll
+                            for (int e = 0; e < JE; e++) {
+                                const int r = lane + 32 * e;
+                                if (r < n) {
+                                    xp[r] = cu_ * cu[u][e] - su_ * cv[u][e];
+                                    xq[r] = su_ * cu[u][e] + cu_ * cv[u][e];
+                                }
+                            }
+                            if (want_u) {
+                                T *jp = J + (size_t) pp[u] * n, *jq = J + (size_t) qq[u] * n;
+                                for (int r = lane; r < n; r += 32) {
+                                    const T ju = jp[r], jv = jq[r];
+                                    jp[r] = cu_ * ju - su_ * jv;
+                                    jq[r] = su_ * ju + cu_ * jv;
+                                }
                             }
                         }
-                        if (lane == 0) s_rot = 1;
                     }
+                    const bool any = rmask != 0;
+                    if (any && lane == 0) s_rot = 1;
                 }
                 __syncthreads();
             }
@@ -313,10 +386,19 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         T *Urj = w, *tauj = w + n * n;
         int e = internal_geqrf<T>(ctx, sidx, m, n, A, lda, sA, tauj, per, batch);
         if (e) return e;
-        GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_rt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         const size_t cap = (size_t) ctx->sm_count * 2;
-        k_jacobi_rt<T><<<(unsigned) (batch < cap ? batch : cap), JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per,
-                                                                                      want_u ? 1 : 0, info, batch, (int) ldx);
+        const unsigned jgrid = (unsigned) (batch < cap ? batch : cap);
+#define GPUB_JACOBI_LAUNCH(JEV)                                                                                              \
+    {                                                                                                                         \
+        GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_rt<T, JEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));         \
+        k_jacobi_rt<T, JEV><<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, want_u ? 1 : 0, info, \
+                                                         batch, (int) ldx);                                                   \
+    }
+        if (n <= 128) GPUB_JACOBI_LAUNCH(4)
+        else if (n <= 192) GPUB_JACOBI_LAUNCH(6)
+        else if (n <= 256) GPUB_JACOBI_LAUNCH(8)
+        else return GPUB_ENOTSUP;
+#undef GPUB_JACOBI_LAUNCH
         GPUB_LAUNCH_CHECK();
         if (want_u) {
             size_t total = m * m * batch;

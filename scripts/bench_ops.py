@@ -123,6 +123,79 @@ def main():
         med, best = timeit(lambda: capi.geqrf_batched(ctx, A, tau), lambda: A.copy_(A0), max(3, args.reps // 2))
         report("geqrf", [m, n], dt, batch, med, best, 2 * m * n * s + n * s, 2 * m * n * n - 2 * n ** 3 / 3, rm)
 
+    def svd(m, n, dt, batch, want_u):
+        tdt = torch.float64 if dt == "f64" else torch.float32
+        s = 8 if dt == "f64" else 4
+        A0 = torch.empty((batch, n, m), dtype=tdt, device="cuda")
+        capi.fill_uniform(ctx, A0, -1.0, 1.0, 9)
+        A = torch.empty_like(A0)
+        rm = None
+        if ref is not None:
+            S = torch.empty((batch, n), dtype=tdt, device="cuda"); Vt = torch.empty((batch, n, n), dtype=tdt, device="cuda")
+            U = torch.empty((batch, m, m), dtype=tdt, device="cuda") if want_u else None
+            ms = C.c_float()
+            ct = C.c_double if dt == "f64" else C.c_float
+            getattr(ref, f"ref_svd_{dt}")(SZ(m), SZ(n), SZ(batch), C.c_void_p(A0.data_ptr()), C.c_void_p(S.data_ptr()), C.c_void_p(Vt.data_ptr()),
+                                          C.c_void_p(U.data_ptr()) if want_u else None, None, None, ct(1e-6), 1, C.byref(ms))
+            rm = ms.value
+            del S, Vt, U
+        # the launcher is timed with its outputs and workspace already allocated (like the reference's factorise())
+        lib = ctx.lib
+        ws = getattr(lib, f"gpub_gesvd_batched_worksize_{dt}")(m, n, ord("A") if want_u else ord("N"), batch)
+        work = torch.empty(ws, dtype=torch.uint8, device="cuda")
+        S = torch.empty((batch, n), dtype=tdt, device="cuda"); Vt = torch.empty((batch, n, n), dtype=tdt, device="cuda")
+        U = torch.empty((batch, m, m), dtype=tdt, device="cuda") if want_u else None
+        info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        def run():
+            ctx.call("gesvd_batched", A, ord("A") if want_u else ord("N"), m, n, capi._p(A), m, m * n, capi._p(S), n,
+                     capi._p(U) if want_u else None, m, m * m, capi._p(Vt), n, n * n, capi._p(work), ws, capi._p(info), batch)
+        med, best = timeit(run, lambda: A.copy_(A0), max(3, args.reps // 2))
+        assert int(info.abs().max()) == 0
+        flops = (4 * m * m * n + 22 * n ** 3) if want_u else (2 * m * n * n + 2 * n ** 3)       # SURVEY.md 8d estimates
+        bytes_ = (m * n + n + n * n + (m * m if want_u else 0)) * s
+        report("gesvd_U" if want_u else "gesvd", [m, n], dt, batch, med, best, bytes_, flops, rm)
+
+    def nullspace(m, n, dt, batch):
+        """Nullspace(a) for fat a (m x n, m <= n) mirrored through the C ABI exactly as include/gpub200/factorisers.cuh does:
+        tr -> gesvd(U) -> count_gt -> nullspace_pack -> aat; then project = batched GEMM with C aliasing B."""
+        tdt = torch.float64 if dt == "f64" else torch.float32
+        s = 8 if dt == "f64" else 4
+        a0 = torch.empty((batch, n, m), dtype=tdt, device="cuda")            # (k, cols, rows) of the fat matrix
+        capi.fill_uniform(ctx, a0, -1.0, 1.0, 10)
+        b0 = torch.empty((batch, 1, n), dtype=tdt, device="cuda"); capi.fill_uniform(ctx, b0, -1.0, 1.0, 11)
+        rb = rp = None
+        if ref is not None:
+            msb, msp = C.c_float(), C.c_float()
+            proj = torch.empty_like(b0)
+            getattr(ref, f"ref_nullspace_{dt}")(SZ(m), SZ(n), SZ(batch), C.c_void_p(a0.data_ptr()), None, C.c_void_p(b0.data_ptr()),
+                                                C.c_void_p(proj.data_ptr()), 1, C.byref(msb), C.byref(msp))
+            rb, rp = msb.value, msp.value
+        lib = ctx.lib
+        ws = getattr(lib, f"gpub_gesvd_batched_worksize_{dt}")(n, m, ord("A"), batch)
+        work = torch.empty(ws, dtype=torch.uint8, device="cuda")
+        at = torch.empty((batch, m, n), dtype=tdt, device="cuda")             # a^T: n x m tall
+        S = torch.empty((batch, m), dtype=tdt, device="cuda"); Vt = torch.empty((batch, m, m), dtype=tdt, device="cuda")
+        U = torch.empty((batch, n, n), dtype=tdt, device="cuda"); info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        rank = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        N = torch.empty((batch, n, n), dtype=tdt, device="cuda"); P = torch.empty((batch, n, n), dtype=tdt, device="cuda")
+        def build():
+            ctx.call("transpose_batched", a0, m, n, capi._p(a0), m * n, capi._p(at), m * n, batch)
+            ctx.call("gesvd_batched", at, ord("A"), n, m, capi._p(at), n, m * n, capi._p(S), m, capi._p(U), n, n * n, capi._p(Vt), m, m * m,
+                     capi._p(work), ws, capi._p(info), batch)
+            rank.zero_()
+            ctx.call("count_gt_batched", S, capi._p(S), m, m, 1e-6, capi._p(rank), batch)
+            ctx.call("nullspace_pack_batched", U, n, capi._p(U), n * n, capi._p(rank), capi._p(N), n * n, batch)
+            ctx.call("aat_batched", N, n, capi._p(N), n * n, capi._p(P), n * n, batch)
+        med, best = timeit(build, lambda: None, max(2, args.reps // 3))
+        assert int(info.abs().max()) == 0
+        report("nullspace", [m, n], dt, batch, med, best, (m * n + 2 * n * n) * s, 4 * n * n * m + 22 * m ** 3 + 2 * n ** 3, rb)
+        b = torch.empty_like(b0)
+        med, best = timeit(lambda: capi.gemm_batched(ctx, b, P, b), lambda: b.copy_(b0), args.reps)
+        report("project", [n, n], dt, batch, med, best, (n * n + 2 * n) * s, 2 * n * n, rp)
+        # property: a * proj == 0
+        x = b.transpose(1, 2)[:4]; r = torch.linalg.norm(torch.bmm(a0[:4].transpose(1, 2), x)) / torch.linalg.norm(b0[:4])
+        assert float(r) < (1e-10 if dt == "f64" else 1e-3), float(r)
+
     sc = args.scale
     if "potrf" in ops or "potrs" in ops:
         chol(32, "f64", int(1_000_000 * sc))
@@ -144,6 +217,12 @@ def main():
         gels(64, 16, "f32", int((1 << 20) * sc))
     if "qr" in ops:
         qr(1024, 128, "f64", 256)
+    if "svd" in ops:
+        svd(1024, 128, "f64", max(2, int(256 * sc)), False)
+    if "svdu" in ops:
+        svd(1024, 128, "f64", max(2, int(256 * sc)), True)
+    if "nullspace" in ops:
+        nullspace(128, 1024, "f64", max(2, int(256 * sc)))
     if args.json:
         Path(args.json).write_text(json.dumps(out, indent=1))
 
