@@ -1028,6 +1028,209 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_sub(T *A, size_t s
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 variant on packed arithmetic: k_gels_f2<M, N, LPM>. Same mapping and the same operations as k_gels_sub, but the
+// RPL = 8 rows of a lane are held as float2 pairs and every dot product / rank-1 update goes through FFMA2
+// (fma.rn.f32x2, two IEEE FMAs per issue slot on sm_100): the kernel is issue-bound, so halving the FMA instruction
+// count is what moves it. larfg and the back substitution use rsqrt / rcp seeds + one Newton step instead of the
+// sqrt / divide slow-path calls (every lane evaluates them redundantly).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_nr(float d) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    return fmaf(fmaf(-d, y, 1.0f), y, y);
+}
+
+#ifndef GPUB_GELS_STAGE
+#define GPUB_GELS_STAGE 0
+#endif
+#ifndef GPUB_GELS_EARLY
+#define GPUB_GELS_EARLY 1
+#endif
+#ifndef GPUB_GELS_L2PF
+#define GPUB_GELS_L2PF 0
+#endif
+__device__ __forceinline__ void gels_cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// The systems of the NEXT iteration are copied global -> shared with cp.async while the current ones are factorised
+// (each lane copies exactly the 16-byte pieces it will read itself, so no cross-lane synchronisation is needed; pieces
+// are laid out [column][piece][lane] so the LDS.128 are bank-conflict free), and column j is stored as soon as step j
+// has finished it: neither the load latency nor the 34 back-to-back STG.128 sit on the critical path any more.
+template<int M, int N, int LPM>
+__global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_t sA, float *b, size_t sB, int *info, size_t batch) {
+    constexpr int RPL = M / LPM;           // rows per lane
+    constexpr int NP = RPL / 2;            // float2 pairs per lane per column
+    constexpr int NV = RPL / 4;            // 128-bit accesses per lane per column
+    static_assert(RPL % 4 == 0, "rows per lane must be a multiple of 4");
+    constexpr int MPC = 128 / LPM;
+    constexpr int SYS4 = (N + 1) * (M / 4); // float4 per system [A | b]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw) + (size_t) (threadIdx.x / LPM) * SYS4;   // this group's system
+    const int l = threadIdx.x % LPM;
+    const int gl = (threadIdx.x & 31) - l;
+    const int row0 = l * RPL;
+    const size_t ngroups = (size_t) gridDim.x * MPC;
+    const size_t iters = (batch + ngroups - 1) / ngroups;
+
+    auto prefetch = [&](size_t it_) {
+        size_t mat = it_ * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
+        if (mat >= batch) mat = batch - 1;
+        const float *a_n = A + mat * sA + row0, *b_n = b + mat * sB + row0;
+#pragma unroll
+        for (int c = 0; c <= N; c++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) gels_cp_async16(&stage[c * (M / 4) + v * LPM + l], (c < N ? a_n + (size_t) c * M : b_n) + 4 * v);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+#if GPUB_GELS_STAGE
+    if (iters > 0) prefetch(0);
+#else
+    (void) stage; (void) prefetch;
+#endif
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
+        float *a_g = A + mat * sA + row0;
+        float *b_g = b + mat * sB + row0;
+        float2 a[N + 1][NP];
+#if GPUB_GELS_STAGE
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+#pragma unroll
+        for (int c = 0; c <= N; c++) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+#if GPUB_GELS_STAGE
+                const float4 x = stage[c * (M / 4) + v * LPM + l];
+#else
+                const float4 x = reinterpret_cast<const float4 *>(c < N ? a_g + (size_t) c * M : b_g)[v];
+#endif
+                a[c][2 * v] = make_float2(x.x, x.y);
+                a[c][2 * v + 1] = make_float2(x.z, x.w);
+            }
+        }
+#if GPUB_GELS_STAGE
+        if (it + 1 < iters) prefetch(it + 1);   // the lane has consumed its own pieces: the slot can be refilled
+#endif
+#if GPUB_GELS_L2PF
+        if (it + 1 < iters) {                   // pull the next system of this lane group into L2 (34 lines of 128 bytes)
+            size_t nm = (it + 1) * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
+            if (nm >= batch) nm = batch - 1;
+            const char *pa = reinterpret_cast<const char *>(A + nm * sA), *pb = reinterpret_cast<const char *>(b + nm * sB);
+            for (int ln = l; ln < (N * M * 4) / 128; ln += LPM) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 128 * ln));
+            if (l < (M * 4) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
+        }
+#endif
+        int bad = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            // |x|^2 over the rows below j
+            float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < NP; t++) {
+                const float2 x = make_float2(row0 + 2 * t > j ? a[j][t].x : 0.f, row0 + 2 * t + 1 > j ? a[j][t].y : 0.f);
+                part = __ffma2_rn(x, x, part);
+            }
+            const float xnorm2 = group_sum<float, LPM>(part.x + part.y);
+            const float ajj = ((j % RPL) & 1) ? a[j][(j % RPL) / 2].y : a[j][(j % RPL) / 2].x;
+            const float alpha = __shfl_sync(0xffffffffu, ajj, gl + j / RPL);
+            float tau = 0.f, scale = 0.f, beta = alpha;
+            if (xnorm2 != 0.f) {
+                const float ss = fmaf(alpha, alpha, xnorm2);
+                float rn = rsqrtf(ss);
+                rn = fmaf(0.5f * rn, fmaf(-ss * rn, rn, 1.0f), rn);
+                float nrm = ss * rn;
+                nrm = fmaf(fmaf(-nrm, nrm, ss), 0.5f * rn, nrm);
+                beta = alpha >= 0.f ? -nrm : nrm;
+                const float rbeta = alpha >= 0.f ? -rn : rn;
+                const float num = beta - alpha;
+                tau = num * rbeta;
+                tau = fmaf(fmaf(-tau, beta, num), rbeta, tau);
+                scale = rcp_nr(alpha - beta);
+            }
+            if (beta == 0.f && bad == 0) bad = j + 1;
+            float2 v[NP];
+#pragma unroll
+            for (int t = 0; t < NP; t++) {
+                const int r0 = row0 + 2 * t, r1 = r0 + 1;
+                v[t] = make_float2(r0 > j ? a[j][t].x * scale : (r0 == j ? 1.f : 0.f), r1 > j ? a[j][t].y * scale : (r1 == j ? 1.f : 0.f));
+                a[j][t] = make_float2(r0 > j ? v[t].x : (r0 == j ? beta : a[j][t].x), r1 > j ? v[t].y : (r1 == j ? beta : a[j][t].y));
+            }
+            if (GPUB_GELS_EARLY && live) {                     // column j is final
+                float4 *dst = reinterpret_cast<float4 *>(a_g + (size_t) j * M);
+#pragma unroll
+                for (int vv = 0; vv < NV; vv++) dst[vv] = make_float4(a[j][2 * vv].x, a[j][2 * vv].y, a[j][2 * vv + 1].x, a[j][2 * vv + 1].y);
+            }
+            float w[N + 1];
+#pragma unroll
+            for (int c = j + 1; c <= N; c++) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < NP; t++) acc = __ffma2_rn(v[t], a[c][t], acc);
+                w[c] = acc.x + acc.y;
+            }
+#pragma unroll
+            for (int c = j + 1; c <= N; c++) w[c] = tau * group_sum<float, LPM>(w[c]);
+#pragma unroll
+            for (int c = j + 1; c <= N; c++) {
+                const float2 nw = make_float2(-w[c], -w[c]);
+#pragma unroll
+                for (int t = 0; t < NP; t++) a[c][t] = __ffma2_rn(nw, v[t], a[c][t]);
+            }
+        }
+        // back substitution on R: row j lives in lane j / RPL, slot j % RPL
+#pragma unroll
+        for (int j = N - 1; j >= 0; j--) {
+            const float bj = ((j % RPL) & 1) ? a[N][(j % RPL) / 2].y : a[N][(j % RPL) / 2].x;
+            const float rjj = ((j % RPL) & 1) ? a[j][(j % RPL) / 2].y : a[j][(j % RPL) / 2].x;
+            const float num = __shfl_sync(0xffffffffu, bj, gl + j / RPL), den = __shfl_sync(0xffffffffu, rjj, gl + j / RPL);
+            const float rden = rcp_nr(den);
+            float xj = num * rden;
+            xj = fmaf(fmaf(-xj, den, num), rden, xj);
+            if (row0 < N) {            // only the lanes that hold rows of R
+#pragma unroll
+                for (int t = 0; t < NP; t++) {
+                    const int r0 = row0 + 2 * t, r1 = r0 + 1;
+                    a[N][t].x = r0 == j ? xj : (r0 < j ? fmaf(-a[j][t].x, xj, a[N][t].x) : a[N][t].x);
+                    a[N][t].y = r1 == j ? xj : (r1 < j ? fmaf(-a[j][t].y, xj, a[N][t].y) : a[N][t].y);
+                }
+            }
+        }
+        if (live) {
+            if (!GPUB_GELS_EARLY) {
+#pragma unroll
+                for (int c = 0; c < N; c++) {
+                    float4 *dc = reinterpret_cast<float4 *>(a_g + (size_t) c * M);
+#pragma unroll
+                    for (int vv = 0; vv < NV; vv++) dc[vv] = make_float4(a[c][2 * vv].x, a[c][2 * vv].y, a[c][2 * vv + 1].x, a[c][2 * vv + 1].y);
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(b_g);
+#pragma unroll
+            for (int vv = 0; vv < NV; vv++) dst[vv] = make_float4(a[N][2 * vv].x, a[N][2 * vv].y, a[N][2 * vv + 1].x, a[N][2 * vv + 1].y);
+            if (info && l == 0) info[mat] = bad;
+        }
+    }
+}
+
+template<typename T, int M, int N, int LPM> struct GelsKernel {
+    static void launch(unsigned grid, cudaStream_t stream, T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
+        k_gels_sub<T, M, N, LPM><<<grid, 128, 0, stream>>>(A, sA, b, sB, info, batch);
+    }
+};
+template<int M, int N, int LPM> struct GelsKernel<float, M, N, LPM> {
+    static void launch(unsigned grid, cudaStream_t stream, float *A, size_t sA, float *b, size_t sB, int *info, size_t batch) {
+        const size_t smem = GPUB_GELS_STAGE ? (size_t) (128 / LPM) * (N + 1) * M * sizeof(float) : 0;   // one staged system per lane group
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gels_f2<M, N, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k_gels_f2<M, N, LPM><<<grid, 128, smem, stream>>>(A, sA, b, sB, info, batch);
+    }
+};
+
 template<typename T>
 size_t qr_smem_bytes(size_t m, size_t n, bool gels) {
     return ((m | 1) * (n + (gels ? 1 : 0))) * sizeof(T);
@@ -1123,14 +1326,17 @@ int launch_gels_sub(gpub_ctx_t ctx, cudaStream_t stream, T *A, size_t sA, T *b, 
     const size_t want = gpub_ceil_div(batch, (size_t) (128 / LPM));
     const size_t cap = (size_t) ctx->sm_count * GPUB_GELS_MINB * 2;
     const unsigned grid = (unsigned) (want < cap ? want : cap);
-    k_gels_sub<T, M, N, LPM><<<grid, 128, 0, stream>>>(A, sA, b, sB, info, batch);
+    GelsKernel<T, M, N, LPM>::launch(grid, stream, A, sA, b, sB, info, batch);
     GPUB_LAUNCH_CHECK();
     return GPUB_OK;
 }
 
 // lanes per matrix: 8 consecutive fp32 rows (or 4 fp64 rows) per lane keeps [A | b] within ~140 registers
 template<typename T> struct GelsLpm;
-template<> struct GelsLpm<float> { static constexpr int rows_per_lane = 8; };
+#ifndef GPUB_GELS_RPL_F32
+#define GPUB_GELS_RPL_F32 8
+#endif
+template<> struct GelsLpm<float> { static constexpr int rows_per_lane = GPUB_GELS_RPL_F32; };
 template<> struct GelsLpm<double> { static constexpr int rows_per_lane = 4; };
 
 template<typename T>
