@@ -516,7 +516,10 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
 }
 
 // G = V^T V, T, and the trailing update A2 <- (I - V T^T V^T) A2 for one panel
-__device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t lda, int n, int j0, int mj, int ldv
+// tgt: matrix whose columns [col0, col_end) are updated on rows j0 .. j0 + mj - 1 (leading dimension ldt). TRT: apply
+// I - V T^T V^T (Q^T, what geqrf needs) when true, I - V T V^T (Q) when false.
+template<bool TRT>
+__device__ __forceinline__ void tcq_trailing(TcqShared sh, double *tgt, size_t ldt, int col0, int col_end, int j0, int mj, int ldv
 #ifdef GPUB_TCQ_PROFILE
                                           , long long &tcq_t0
 #endif
@@ -524,7 +527,7 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t l
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     const int mj16 = (mj + 15) & ~15;
-    const int ntrail = n - (j0 + TCQ_NB);
+    const int ntrail = col_end - col0;
     const unsigned vs_sh = (unsigned) __cvta_generic_to_shared(sh.Vs());
     const unsigned v8off = (unsigned) (8 * ldv * 8);   // byte offset of V column c + 8
     const int ncb = (ntrail + 7) / 8;
@@ -536,9 +539,9 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t l
         const int r0 = rg * rpg;
 #pragma unroll
         for (int sl = 0; sl < TCQ_NSL; sl++) {
-            const int cb = cbs + cq + 4 * sl, col = j0 + TCQ_NB + 8 * cb + (lane & 7);
-            if (cb < ncb && col < n) {
-                const double *base = a_g + (size_t) j0 + (size_t) col * lda + r0;
+            const int cb = cbs + cq + 4 * sl, col = col0 + 8 * cb + (lane & 7);
+            if (cb < ncb && col < col_end) {
+                const double *base = tgt + (size_t) j0 + (size_t) col * ldt + r0;
                 for (int ln = lane >> 3; 16 * ln < rpg && r0 + 16 * ln < mj; ln += 4)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 16 * ln));
             }
@@ -606,9 +609,9 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t l
             const double *a2[TCQ_NSL];
 #pragma unroll
             for (int sl = 0; sl < TCQ_NSL; sl++) {
-                const int cb = cb0 + cq + 4 * sl, c0 = j0 + TCQ_NB + 8 * cb;
-                const bool ok = cb < ncb && c0 + g < n;
-                a2[sl] = a_g + (size_t) j0 + (size_t) (ok ? c0 + g : j0) * lda + 2 * q + r0;
+                const int cb = cb0 + cq + 4 * sl, c0 = col0 + 8 * cb;
+                const bool ok = cb < ncb && c0 + g < col_end;
+                a2[sl] = tgt + (size_t) j0 + (size_t) (ok ? c0 + g : col0) * ldt + 2 * q + r0;
             }
             double acc[TCQ_NSL][2][2];
 #pragma unroll
@@ -691,7 +694,7 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t l
 #pragma unroll
                 for (int kk = 0; kk < TCQ_NB; kk++) {
                     const int k = (kk + 2 * c) & 15;
-                    const double t = k <= i ? sh.Ts()[k * 17 + i] : 0.0;
+                    const double t = TRT ? (k <= i ? sh.Ts()[k * 17 + i] : 0.0) : (k >= i ? sh.Ts()[i * 17 + k] : 0.0);
                     acc = fma(t, wc[kk], acc);
                 }
                 sh.wp()[(size_t) warp * (8 * TCQ_LDW) + c * TCQ_LDW + i] = -acc;
@@ -713,13 +716,13 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *a_g, size_t l
             unsigned okmask = 0;      // bit sl: this lane's column of slot sl exists and is stored
 #pragma unroll
             for (int sl = 0; sl < TCQ_NSL; sl++) {
-                const int cbl = cq + 4 * sl, cb = cb0 + cbl, c0 = j0 + TCQ_NB + 8 * cb;
+                const int cbl = cq + 4 * sl, cb = cb0 + cbl, c0 = col0 + 8 * cb;
                 const bool live = cb < ncb;
-                const bool ok = live && c0 + g < n;
+                const bool ok = live && c0 + g < col_end;
                 okmask |= (ok ? 1u : 0u) << sl;
 #pragma unroll
                 for (int s4 = 0; s4 < 4; s4++) bw[sl][s4] = live ? sh.wp()[(size_t) cbl * (8 * TCQ_LDW) + g * TCQ_LDW + 4 * s4 + q] : 0.0;
-                cp[sl] = a_g + (size_t) j0 + (size_t) (ok ? c0 + g : j0) * lda + 2 * q + 16 * b0;
+                cp[sl] = tgt + (size_t) j0 + (size_t) (ok ? c0 + g : col0) * ldt + 2 * q + 16 * b0;
             }
             unsigned vaa = vs_sh + (unsigned) ((q * ldv + g + 16 * b0) * 8);
             const unsigned s4off = (unsigned) (4 * ldv * 8);
@@ -830,7 +833,7 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
             if (ntrail <= 0) { __syncthreads(); continue; }
             __syncthreads();
             TCQ_T(2);
-            tcq_trailing(sh, a_g, lda, n, j0, mj, ldv
+            tcq_trailing<true>(sh, a_g, lda, j0 + TCQ_NB, n, j0, mj, ldv
 #ifdef GPUB_TCQ_PROFILE
                          , tcq_t0
 #endif
@@ -839,6 +842,89 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
             TCQ_T(6);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// C <- Q C or Q^T C with Q = H_0 ... H_{k-1} from geqrf, blocked: k_ormqr_tc<TRANS>, fp64, m <= 1024.
+// One CTA per (matrix, chunk of 64 columns of C). For every panel of 16 reflectors (last to first for Q, first to last for
+// Q^T) the CTA rebuilds the explicit V panel in shared memory from the factored matrix, recomputes T from V^T V and tau
+// (cheaper than storing 16 x 16 factors per panel), and applies I - V T V^T (or T^T) with the same two DMMA passes as the
+// trailing update of k_geqrf_tc. Replaces the column-by-column k_ormqr_cta for the U assembly of Svd / Nullspace and getQR.
+// ------------------------------------------------------------------------------------------
+template<bool TRANS>
+__global__ void __launch_bounds__(TCQ_THREADS, 1) k_ormqr_tc(int m, int ncols, int k, const double *__restrict__ A, size_t lda, size_t sA,
+                                                              const double *__restrict__ tau, size_t sTau, double *C, size_t ldc, size_t sC,
+                                                              size_t batch, int chunks, int cols_per_chunk, int ldv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TcqShared sh;
+    sh.base = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int npan = (k + TCQ_NB - 1) / TCQ_NB;
+    for (size_t t = blockIdx.x; t < batch * (size_t) chunks; t += gridDim.x) {
+        const size_t mat = t / chunks;
+        const int ch = (int) (t - mat * chunks);
+        const double *a_g = A + mat * sA;
+        const double *tau_g = tau + mat * sTau;
+        double *c_g = C + mat * sC;
+        const int col0 = ch * cols_per_chunk;
+        const int col_end = (col0 + cols_per_chunk) < ncols ? (col0 + cols_per_chunk) : ncols;
+#ifdef GPUB_TCQ_PROFILE
+        long long tcq_t0 = clock64();
+#endif
+        for (int pi = 0; pi < npan; pi++) {
+            const int p = TRANS ? pi : npan - 1 - pi;
+            const int j0 = p * TCQ_NB;
+            const int nb = (k - j0) < TCQ_NB ? (k - j0) : TCQ_NB;
+            const int mj = m - j0, mj16 = (mj + 15) & ~15;
+            for (int r = tid; r < mj16; r += TCQ_THREADS) {
+#pragma unroll
+                for (int c = 0; c < TCQ_NB; c++) {
+                    double v = 0.0;
+                    if (r < mj && c < nb) v = r > c ? a_g[(size_t) (j0 + r) + (size_t) (j0 + c) * lda] : (r == c ? 1.0 : 0.0);
+                    sh.Vs()[(size_t) c * ldv + r] = v;
+                }
+            }
+            if (tid < TCQ_NB) sh.taus()[tid] = tid < nb ? tau_g[j0 + tid] : 0.0;
+            __syncthreads();
+            tcq_trailing<TRANS>(sh, c_g, ldc, col0, col_end, j0, mj, ldv
+#ifdef GPUB_TCQ_PROFILE
+                                , tcq_t0
+#endif
+            );
+            __syncthreads();
+        }
+    }
+}
+
+template<typename T>
+bool try_ormqr_tc(gpub_ctx_t, cudaStream_t, int, size_t, size_t, size_t, const T *, size_t, size_t, const T *, size_t, T *, size_t, size_t, size_t, int *) {
+    return false;
+}
+template<>
+bool try_ormqr_tc<double>(gpub_ctx_t ctx, cudaStream_t stream, int trans, size_t m, size_t ncols, size_t k, const double *A, size_t lda, size_t sA,
+                          const double *tau, size_t sTau, double *C, size_t ldc, size_t sC, size_t batch, int *err) {
+    if (m > 1024 || m < 64 || ncols < 16 || (ncols & 1) || k < 8) return false;
+    if ((ldc & 1) || (sC & 1) || (((uintptr_t) C) & 15u)) return false;
+    const size_t ldv = (m + 15) / 16 * 16 + 8;
+    const size_t smem = ((size_t) TCQ_OFF_VS + TCQ_NB * ldv) * sizeof(double);
+    if (smem > (size_t) ctx->max_smem_optin) return false;
+    const int cols_per_chunk = 8 * 4 * TCQ_NSL;
+    const size_t chunks = gpub_ceil_div(ncols, (size_t) cols_per_chunk), total = chunks * batch, cap = (size_t) ctx->sm_count * 8;
+    const unsigned grid = (unsigned) (total < cap ? total : cap);
+    cudaError_t e;
+    if (trans) {
+        e = cudaFuncSetAttribute(k_ormqr_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess)
+            k_ormqr_tc<true><<<grid, TCQ_THREADS, smem, stream>>>((int) m, (int) ncols, (int) k, A, lda, sA, tau, sTau, C, ldc, sC, batch, (int) chunks,
+                                                                  cols_per_chunk, (int) ldv);
+    } else {
+        e = cudaFuncSetAttribute(k_ormqr_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess)
+            k_ormqr_tc<false><<<grid, TCQ_THREADS, smem, stream>>>((int) m, (int) ncols, (int) k, A, lda, sA, tau, sTau, C, ldc, sC, batch, (int) chunks,
+                                                                   cols_per_chunk, (int) ldv);
+    }
+    *err = e == cudaSuccess ? GPUB_OK : (int) e;
+    return true;
 }
 
 template<typename T>
@@ -1288,6 +1374,14 @@ int ormqr_batched(gpub_ctx_t ctx, int sidx, int trans, size_t m, size_t ncols, s
     if (m == 0 || ncols == 0 || k == 0 || batch == 0) return GPUB_OK;
     if (!A || !tau || !C || lda < m || ldc < m || k > m) return GPUB_EINVAL;
     GPUB_ENTER(ctx, sidx);
+    {
+        int etc = GPUB_OK;
+        if (try_ormqr_tc<T>(ctx, stream, trans, m, ncols, k, A, lda, sA, tau, sTau, C, ldc, sC, batch, &etc)) {
+            if (etc != GPUB_OK) return etc;
+            GPUB_LAUNCH_CHECK();
+            return GPUB_OK;
+        }
+    }
     // split the columns of C over several CTAs when the batch alone cannot fill the GPU
     size_t col_blocks = 1;
     const size_t wpb = QT / 32;
