@@ -794,6 +794,80 @@ __global__ void __launch_bounds__(GEMV_ROWS * GEMV_KS) k_gemv(size_t m, size_t k
     }
 }
 
+// Vectorised variant for aligned operands (m a multiple of the CTA's row block, 16-byte aligned A, lda % VN == 0):
+// a thread owns VN consecutive rows (one 128-bit load per column) and one of 8 contiguous k-slices, x comes from shared
+// memory two / four values at a time. 32 x 8 threads per CTA.
+constexpr int GEMV2_KS = 8;
+
+template<typename T>
+__global__ void __launch_bounds__(32 * GEMV2_KS) k_gemv_vec(size_t m, size_t k, T alpha, const T *__restrict__ A, size_t lda, size_t sA,
+                                                             const T *__restrict__ x, size_t sX, T beta, T *y, size_t sY, size_t row_blocks,
+                                                             size_t batch) {
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::N;
+    constexpr int RB = 32 * VN;
+    __shared__ __align__(16) T xs[GEMV_XCHUNK];
+    __shared__ T part[GEMV2_KS][RB];
+    const int r = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    for (size_t t = blockIdx.x; t < batch * row_blocks; t += gridDim.x) {
+        const size_t mat = t / row_blocks, rb = t - mat * row_blocks;
+        const T *a = A + mat * sA + rb * RB + (size_t) r * VN;
+        const T *xg = x + mat * sX;
+        T acc[VN];
+#pragma unroll
+        for (int e = 0; e < VN; e++) acc[e] = T(0);
+        for (size_t k0 = 0; k0 < k; k0 += GEMV_XCHUNK) {
+            const size_t kc = (k - k0) < (size_t) GEMV_XCHUNK ? (k - k0) : (size_t) GEMV_XCHUNK;
+            __syncthreads();
+            for (size_t j = threadIdx.x; j < kc; j += blockDim.x) xs[j] = xg[k0 + j];
+            __syncthreads();
+            // slice [j0, j1) of this chunk, boundaries multiples of 4 columns
+            const size_t per = ((kc + GEMV2_KS - 1) / GEMV2_KS + 3) & ~(size_t) 3;
+            const size_t j0 = (size_t) ks * per < kc ? (size_t) ks * per : kc;
+            const size_t j1 = j0 + per < kc ? j0 + per : kc;
+            const T *ac = a + (k0 + j0) * lda;
+            size_t j = j0;
+#pragma unroll 2
+            for (; j + 4 <= j1; j += 4, ac += 4 * lda) {
+                V v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const V *>(ac + (size_t) u * lda);
+                T xv[4];
+                if constexpr (VN == 2) {
+                    const double2 x01 = *reinterpret_cast<const double2 *>(&xs[j]), x23 = *reinterpret_cast<const double2 *>(&xs[j + 2]);
+                    xv[0] = x01.x; xv[1] = x01.y; xv[2] = x23.x; xv[3] = x23.y;
+                } else {
+                    const float4 x4 = *reinterpret_cast<const float4 *>(&xs[j]);
+                    xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    T av[VN];
+                    unpack_v(v[u], av);
+#pragma unroll
+                    for (int e = 0; e < VN; e++) acc[e] = fma(av[e], xv[u], acc[e]);
+                }
+            }
+            for (; j < j1; j++, ac += lda) {
+                T av[VN];
+                unpack_v(*reinterpret_cast<const V *>(ac), av);
+#pragma unroll
+                for (int e = 0; e < VN; e++) acc[e] = fma(av[e], xs[j], acc[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < VN; e++) part[ks][r * VN + e] = acc[e];
+        __syncthreads();
+        for (int rr = threadIdx.x; rr < RB; rr += blockDim.x) {
+            T sum = T(0);
+#pragma unroll
+            for (int q = 0; q < GEMV2_KS; q++) sum += part[q][rr];
+            T *yp = y + mat * sY + rb * RB + rr;
+            *yp = beta == T(0) ? alpha * sum : alpha * sum + beta * (*yp);
+        }
+    }
+}
+
 template<typename T> struct UseDmma { static constexpr bool value = false; };
 template<> struct UseDmma<double> { static constexpr bool value = true; };
 
@@ -899,10 +973,17 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
     const unsigned grid = (unsigned) (total < cap ? total : cap);
     bool done = false;
     if (n == 1 && k > 0) {
-        const size_t row_blocks = gpub_ceil_div(m, (size_t) GEMV_ROWS), items = row_blocks * batch;
+        constexpr size_t RBV = 32 * Vec16<T>::N;
         const size_t vcap = (size_t) ctx->sm_count * 16;
-        k_gemv<T><<<(unsigned) (items < vcap ? items : vcap), GEMV_ROWS * GEMV_KS, 0, stream>>>(m, k, alpha, A, lda, sA, B, sB, beta, C, sC,
-                                                                                                  row_blocks, batch);
+        if (m % RBV == 0 && lda % Vec16<T>::N == 0 && sA % Vec16<T>::N == 0 && (((uintptr_t) A) & 15u) == 0 && k >= 32) {
+            const size_t row_blocks = m / RBV, items = row_blocks * batch;
+            k_gemv_vec<T><<<(unsigned) (items < vcap ? items : vcap), 32 * GEMV2_KS, 0, stream>>>(m, k, alpha, A, lda, sA, B, sB, beta, C, sC,
+                                                                                                    row_blocks, batch);
+        } else {
+            const size_t row_blocks = gpub_ceil_div(m, (size_t) GEMV_ROWS), items = row_blocks * batch;
+            k_gemv<T><<<(unsigned) (items < vcap ? items : vcap), GEMV_ROWS * GEMV_KS, 0, stream>>>(m, k, alpha, A, lda, sA, B, sB, beta, C, sC,
+                                                                                                      row_blocks, batch);
+        }
         done = true;
     }
     if (!done && UseDmma<T>::value) {
