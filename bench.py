@@ -134,6 +134,9 @@ def cpu_baseline(A_host, b_host, sample: int):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: everything libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -166,7 +169,8 @@ def main():
     if args.impl == "reference":
         ref_path = REPO / "oracle" / "_ref" / "libgputils_ref.so"
         if not ref_path.exists():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgputils_ref.so not built (make -C oracle ref)"}))
+            real_stdout.write(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgputils_ref.so not built (make -C oracle ref)"}) + "\n")
+            real_stdout.flush()
             return 0
         ref = C.CDLL(str(ref_path))
 
@@ -336,10 +340,10 @@ def main():
                           "solve_matrices_per_s": (world if args.impl == "ours" else 1) * k / ((total_ms - factor_ms_sum) / args.steps * 1e-3),
                           "factorise_gflops": (world if args.impl == "ours" else 1) * k * 11440 / (potrf_ms * 1e-3) / 1e9,
                           "solve_hbm_gbs": potrs_bytes / ((total_ms - factor_ms_sum) / args.steps * 1e-3) / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "k_potrf_group<double,32>" if args.impl == "ours" else "cusolverDnDpotrfBatched",
+            "roofline": {"bound": "hbm", "kernel": "k_potrf32_pair<double>" if args.impl == "ours" else "cusolverDnDpotrfBatched",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (POTRF_DRAM_BYTES_PER_MATRIX * k if args.impl == "ours" else None),
-                         "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_potrf_group<double,32>: "
+                         "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the potrf kernel: "
                                             "profiles/r1c_ncu_chol_n32_f64.json (only the lower triangle moves)" if args.impl == "ours" else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": potrf_bytes,
                          "frac_of_8TBs_nominal": achieved / 8000.0},
@@ -351,7 +355,8 @@ def main():
         if args.impl == "reference":
             line["impl"] = "reference"
             line["reference"] = "GPUtils include/tensor.cuh (unmodified) + cuBLAS/cuSOLVER 12.9, CholeskyBatchFactoriser::factorise/solve, same GPU"
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if use_dist:
         dist.destroy_process_group()
     return 0

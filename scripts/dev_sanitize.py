@@ -1,0 +1,29 @@
+"""Small invocations of every kernel family, meant to be run under compute-sanitizer (memcheck / racecheck / synccheck):
+   compute-sanitizer --tool racecheck python scripts/dev_sanitize.py"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from gputils_b200 import capi
+ctx = capi.Context()
+rng = np.random.default_rng(0)
+def spd(n, k, dt):
+    G = rng.uniform(-1, 1, (k, n, n)); return (G @ G.transpose(0, 2, 1) + n * np.eye(n)).astype(dt)
+for dt in (np.float64, np.float32):
+    for n, k in [(8, 40), (32, 9), (64, 5), (100, 3), (128, 3)]:
+        A = capi.from_numpy_batch(spd(n, k, dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (k, n, 1)).astype(dt))
+        info = torch.zeros(k, dtype=torch.int32, device="cuda")
+        capi.potrf_batched(ctx, A, info); capi.potrs_batched(ctx, A, b)
+    for (m, n, kk, k) in [(8, 8, 8, 50), (32, 32, 32, 9), (64, 64, 64, 3), (128, 128, 128, 2), (256, 1, 256, 3), (100, 1, 70, 3)]:
+        A = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, kk)).astype(dt)); B = capi.from_numpy_batch(rng.uniform(-1, 1, (k, kk, n)).astype(dt))
+        Cm = torch.zeros((k, n, m), dtype=A.dtype, device="cuda"); capi.gemm_batched(ctx, Cm, A, B)
+    A = capi.from_numpy_batch(rng.uniform(-1, 1, (9, 64, 16)).astype(dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (9, 64, 1)).astype(dt))
+    capi.gels_batched(ctx, A, b)
+for (m, n, k) in [(1024, 128, 2), (300, 40, 2), (513, 38, 1)]:
+    A = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, n))); tau = torch.zeros((k, n), dtype=torch.float64, device="cuda")
+    capi.geqrf_batched(ctx, A, tau)
+    Cq = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, 48)))
+    capi.ormqr_batched(ctx, False, A, tau, Cq); capi.ormqr_batched(ctx, True, A, tau, Cq)
+S, U, Vt, info = capi.gesvd_batched(ctx, capi.from_numpy_batch(rng.uniform(-1, 1, (2, 256, 64))), True)
+S, U, Vt, info = capi.gesvd_batched(ctx, capi.from_numpy_batch(rng.uniform(-1, 1, (2, 200, 100)).astype(np.float32)), False)
+torch.cuda.synchronize()
+print("done")
