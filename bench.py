@@ -340,7 +340,7 @@ def main():
                           "solve_matrices_per_s": (world if args.impl == "ours" else 1) * k / ((total_ms - factor_ms_sum) / args.steps * 1e-3),
                           "factorise_gflops": (world if args.impl == "ours" else 1) * k * 11440 / (potrf_ms * 1e-3) / 1e9,
                           "solve_hbm_gbs": potrs_bytes / ((total_ms - factor_ms_sum) / args.steps * 1e-3) / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "k_potrf32_pair<double>" if args.impl == "ours" else "cusolverDnDpotrfBatched",
+            "roofline": {"bound": "hbm", "kernel": "k_potrf_pair<double,32>" if args.impl == "ours" else "cusolverDnDpotrfBatched",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (POTRF_DRAM_BYTES_PER_MATRIX * k if args.impl == "ours" else None),
                          "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the potrf kernel: "

@@ -100,7 +100,7 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 }
 
 // ------------------------------------------------------------------------------------------
-// potrf, n == 32 dense (BASELINE config 2): k_potrf32_pair<T>. 16 lanes per matrix, lane p owns rows p AND p + 16.
+// potrf, n == 32 (BASELINE config 2) or 16, dense: k_potrf_pair<T, N>. N / 2 lanes per matrix, lane p owns rows p AND p + N / 2.
 // k_potrf_group<T, 32> (lane = row) executes 31 - j FMA instructions per column step for every row, although row i only
 // needs columns <= i: n^3/2 lane-FMAs for n^3/6 useful ones, and ncu shows it FP64-issue bound (pipe 48 %, issue 49 %) at
 // 55 % of DRAM throughput. Pairing a short row with a long one skips the columns >= 16 of the short row statically
@@ -110,11 +110,13 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 #ifndef GPUB_POTRF32_MINB
 #define GPUB_POTRF32_MINB 4
 #endif
-template<typename T>
-__global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf32_pair(T *A, size_t strideA, int *info, size_t batch) {
-    constexpr int GROUPS = 128 / 16;
-    __shared__ __align__(16) T s_col[2][GROUPS][32];
-    const int grp = threadIdx.x >> 4, p = threadIdx.x & 15;
+// N = 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H
+template<typename T, int N>
+__global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf_pair(T *A, size_t strideA, int *info, size_t batch) {
+    constexpr int H = N / 2;
+    constexpr int GROUPS = 128 / H;
+    __shared__ __align__(16) T s_col[2][GROUPS][N];
+    const int grp = threadIdx.x / H, p = threadIdx.x % H;
     const size_t ngroups = (size_t) gridDim.x * GROUPS;
     const size_t iters = (batch + ngroups - 1) / ngroups;
     for (size_t it = 0; it < iters; it++) {
@@ -122,15 +124,15 @@ __global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf32_pair(T *A, s
         const bool live = mat < batch;
         if (!live) mat = batch - 1;
         T *a_g = A + mat * strideA;
-        T lo[16], hi[32];   // row p (columns 0..15), row p + 16 (columns 0..31); only the lower triangle is read
+        T lo[H], hi[N];   // row p (columns 0..H-1), row p + H (all columns); only the lower triangle is read
 #pragma unroll
-        for (int c = 0; c < 16; c++) lo[c] = c <= p ? a_g[p + c * 32] : T(0);
+        for (int c = 0; c < H; c++) lo[c] = c <= p ? a_g[p + c * N] : T(0);
 #pragma unroll
-        for (int c = 0; c < 32; c++) hi[c] = c <= p + 16 ? a_g[p + 16 + c * 32] : T(0);
+        for (int c = 0; c < N; c++) hi[c] = c <= p + H ? a_g[p + H + c * N] : T(0);
         int bad = 0;
 #pragma unroll
-        for (int j = 0; j < 16; j++) {          // pivots in the short rows
-            const T d = __shfl_sync(0xffffffffu, lo[j], j, 16);
+        for (int j = 0; j < H; j++) {          // pivots in the short rows
+            const T d = __shfl_sync(0xffffffffu, lo[j], j, H);
             if (!(d > T(0)) && bad == 0) bad = j + 1;
             const T r = fast_rsqrt<T>(d);
             T *col = s_col[j & 1][grp];
@@ -138,37 +140,37 @@ __global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf32_pair(T *A, s
             lo[j] = llo;
             hi[j] = lhi;
             col[p] = llo;
-            col[p + 16] = lhi;
+            col[p + H] = lhi;
             __syncwarp();
 #pragma unroll
-            for (int c = j + 1; c < 16; c++) {
+            for (int c = j + 1; c < H; c++) {
                 const T cc = col[c];
                 lo[c] = fma(-llo, cc, lo[c]);
                 hi[c] = fma(-lhi, cc, hi[c]);
             }
 #pragma unroll
-            for (int c = 16; c < 32; c++) hi[c] = fma(-lhi, col[c], hi[c]);
+            for (int c = H; c < N; c++) hi[c] = fma(-lhi, col[c], hi[c]);
         }
 #pragma unroll
-        for (int j = 16; j < 32; j++) {         // pivots in the long rows; the short rows are finished
-            const T d = __shfl_sync(0xffffffffu, hi[j], j - 16, 16);
+        for (int j = H; j < N; j++) {         // pivots in the long rows; the short rows are finished
+            const T d = __shfl_sync(0xffffffffu, hi[j], j - H, H);
             if (!(d > T(0)) && bad == 0) bad = j + 1;
             const T r = fast_rsqrt<T>(d);
             T *col = s_col[j & 1][grp];
             const T lhi = hi[j] * r;
             hi[j] = lhi;
-            col[p + 16] = lhi;
+            col[p + H] = lhi;
             __syncwarp();
 #pragma unroll
-            for (int c = j + 1; c < 32; c++) hi[c] = fma(-lhi, col[c], hi[c]);
+            for (int c = j + 1; c < N; c++) hi[c] = fma(-lhi, col[c], hi[c]);
         }
         if (live) {
 #pragma unroll
-            for (int c = 0; c < 16; c++)
-                if (c <= p) a_g[p + c * 32] = lo[c];
+            for (int c = 0; c < H; c++)
+                if (c <= p) a_g[p + c * N] = lo[c];
 #pragma unroll
-            for (int c = 0; c < 32; c++)
-                if (c <= p + 16) a_g[p + 16 + c * 32] = hi[c];
+            for (int c = 0; c < N; c++)
+                if (c <= p + H) a_g[p + H + c * N] = hi[c];
             if (p == 0) info[mat] = bad;
         }
         __syncwarp();
@@ -715,9 +717,11 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
 #define GPUB_POTRF_CASE(NPV)                                                                              \
     if (dense) k_potrf_group<T, NPV, true><<<grid, TH, 0, stream>>>((int) n, A, lda, strideA, info, batch); \
     else k_potrf_group<T, NPV, false><<<grid, TH, 0, stream>>>((int) n, A, lda, strideA, info, batch);
-        if (dense && n == 32) {
-            const size_t want32 = gpub_ceil_div(batch, (size_t) 8), cap32 = (size_t) ctx->sm_count * GPUB_POTRF32_MINB * 2;
-            k_potrf32_pair<T><<<(unsigned) (want32 < cap32 ? want32 : cap32), 128, 0, stream>>>(A, strideA, info, batch);
+        if (dense && (n == 32 || n == 16)) {
+            const size_t want32 = gpub_ceil_div(batch, (size_t) (256 / n)), cap32 = (size_t) ctx->sm_count * GPUB_POTRF32_MINB * 2;
+            const unsigned g32 = (unsigned) (want32 < cap32 ? want32 : cap32);
+            if (n == 32) k_potrf_pair<T, 32><<<g32, 128, 0, stream>>>(A, strideA, info, batch);
+            else k_potrf_pair<T, 16><<<g32, 128, 0, stream>>>(A, strideA, info, batch);
             GPUB_LAUNCH_CHECK();
             return GPUB_OK;
         }
