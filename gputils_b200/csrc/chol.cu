@@ -110,12 +110,18 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 #ifndef GPUB_POTRF32_MINB
 #define GPUB_POTRF32_MINB 4
 #endif
-// N = 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H
-template<typename T, int N>
-__global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf_pair(T *A, size_t strideA, int *info, size_t batch) {
+// N = 64, 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H. N = 64 is a whole warp per matrix with the
+// lower triangle in registers (96 entries per lane): no CTA barrier at all, which is what k_potrf_blk loses its time on.
+// DENSE: n == N and lda == N; otherwise rows / columns beyond n are an identity pad and lda is a run-time value.
+template<typename T, int N, bool DENSE = true> struct PotrfPairMinB { static constexpr int value = N == 64 ? (sizeof(T) == 8 ? 2 : (DENSE ? 4 : 3)) : GPUB_POTRF32_MINB; };
+
+template<typename T, int N, bool DENSE>
+__global__ void __launch_bounds__(128, PotrfPairMinB<T, N, DENSE>::value) k_potrf_pair(int n_rt, T *A, size_t lda_rt, size_t strideA, int *info, size_t batch) {
     constexpr int H = N / 2;
     constexpr int GROUPS = 128 / H;
     __shared__ __align__(16) T s_col[2][GROUPS][N];
+    const int n = DENSE ? N : n_rt;
+    const size_t lda = DENSE ? (size_t) N : lda_rt;
     const int grp = threadIdx.x / H, p = threadIdx.x % H;
     const size_t ngroups = (size_t) gridDim.x * GROUPS;
     const size_t iters = (batch + ngroups - 1) / ngroups;
@@ -126,9 +132,9 @@ __global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf_pair(T *A, siz
         T *a_g = A + mat * strideA;
         T lo[H], hi[N];   // row p (columns 0..H-1), row p + H (all columns); only the lower triangle is read
 #pragma unroll
-        for (int c = 0; c < H; c++) lo[c] = c <= p ? a_g[p + c * N] : T(0);
+        for (int c = 0; c < H; c++) lo[c] = (c <= p && (DENSE || p < n)) ? a_g[p + c * lda] : T((!DENSE && c == p) ? 1 : 0);
 #pragma unroll
-        for (int c = 0; c < N; c++) hi[c] = c <= p + H ? a_g[p + H + c * N] : T(0);
+        for (int c = 0; c < N; c++) hi[c] = (c <= p + H && (DENSE || p + H < n)) ? a_g[p + H + c * lda] : T((!DENSE && c == p + H) ? 1 : 0);
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < H; j++) {          // pivots in the short rows
@@ -167,10 +173,10 @@ __global__ void __launch_bounds__(128, GPUB_POTRF32_MINB) k_potrf_pair(T *A, siz
         if (live) {
 #pragma unroll
             for (int c = 0; c < H; c++)
-                if (c <= p) a_g[p + c * N] = lo[c];
+                if (c <= p && (DENSE || p < n)) a_g[p + c * lda] = lo[c];
 #pragma unroll
             for (int c = 0; c < N; c++)
-                if (c <= p + H) a_g[p + H + c * N] = hi[c];
+                if (c <= p + H && (DENSE || p + H < n)) a_g[p + H + c * lda] = hi[c];
             if (p == 0) info[mat] = bad;
         }
         __syncwarp();
@@ -720,8 +726,8 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
         if (dense && (n == 32 || n == 16)) {
             const size_t want32 = gpub_ceil_div(batch, (size_t) (256 / n)), cap32 = (size_t) ctx->sm_count * GPUB_POTRF32_MINB * 2;
             const unsigned g32 = (unsigned) (want32 < cap32 ? want32 : cap32);
-            if (n == 32) k_potrf_pair<T, 32><<<g32, 128, 0, stream>>>(A, strideA, info, batch);
-            else k_potrf_pair<T, 16><<<g32, 128, 0, stream>>>(A, strideA, info, batch);
+            if (n == 32) k_potrf_pair<T, 32, true><<<g32, 128, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+            else k_potrf_pair<T, 16, true><<<g32, 128, 0, stream>>>((int) n, A, lda, strideA, info, batch);
             GPUB_LAUNCH_CHECK();
             return GPUB_OK;
         }
@@ -732,6 +738,12 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
             default: GPUB_POTRF_CASE(32) break;
         }
 #undef GPUB_POTRF_CASE
+    } else if (n <= 64) {
+        // a warp per matrix, the triangle in registers (k_potrf_pair<T, 64>): 4 matrices per CTA
+        const size_t want = gpub_ceil_div(batch, (size_t) 4), cap = (size_t) ctx->sm_count * PotrfPairMinB<T, 64>::value * 2;
+        const unsigned grid = (unsigned) (want < cap ? want : cap);
+        if (n == 64 && lda == 64) k_potrf_pair<T, 64, true><<<grid, 128, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+        else k_potrf_pair<T, 64, false><<<grid, 128, 0, stream>>>((int) n, A, lda, strideA, info, batch);
     } else if (n <= 128) {
         const size_t cap = (size_t) ctx->sm_count * 8;
         const unsigned grid = (unsigned) (batch < cap ? batch : cap);
