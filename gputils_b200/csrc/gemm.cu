@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
 // load gives 4 consecutive k for one column), so 4 k-steps cost TM/4*4 + TN LDS.128 for 4*TM*TN FFMA.
 // Requires m % BM == 0, n % BN == 0, k % 16 == 0 and 16-byte aligned operands (the launcher checks).
 // ------------------------------------------------------------------------------------------
-template<int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm_rt(size_t m, size_t n, size_t k, float alpha, const float *__restrict__ A,
+template<int BM, int BN, int TM, int TN, int MINB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), MINB) k_sgemm_rt(size_t m, size_t n, size_t k, float alpha, const float *__restrict__ A,
                                                                     size_t lda, size_t sA, const float *__restrict__ B, size_t ldb, size_t sB,
                                                                     float beta, float *C, size_t ldc, size_t sC, size_t tiles_m, size_t tiles_n,
                                                                     size_t batch) {
@@ -475,11 +475,13 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm_rt(size_t m, si
         const size_t row0 = (r % tiles_m) * BM, col0 = (r / tiles_m) * BN;
         const float *a = A + b * sA + row0;
         const float *bb = B + b * sB + col0 * ldb;
-        float acc[TN][TM];
+        // accumulators as row pairs: every update is an FFMA2 (fma.rn.f32x2, two IEEE FMAs per issue slot) of a natural pair
+        // of A rows with a duplicated B value -- the kernel is issue-bound, FFMA2 frees the slots the LDS need
+        float2 acc[TN][TM / 2];
 #pragma unroll
         for (int j = 0; j < TN; j++)
 #pragma unroll
-            for (int i = 0; i < TM; i++) acc[j][i] = 0.f;
+            for (int i = 0; i < TM / 2; i++) acc[j][i] = make_float2(0.f, 0.f);
 
         auto load_panel = [&](int buf, size_t k0) {
             // A: BK columns of BM rows -> BK*BM/4 16-byte pieces
@@ -516,18 +518,21 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm_rt(size_t m, si
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
-                    float av[TM];
+                    float2 av[TM / 2];
 #pragma unroll
                     for (int i = 0; i < TM; i += 4) {
                         // rows of a thread are TM/4 groups of 4, the groups BM/(TM/4) apart: consecutive threads read
                         // consecutive 16-byte pieces (conflict-free)
                         const float4 v = *reinterpret_cast<const float4 *>(&As[buf][k4 + kk][(i / 4) * (BM / (TM / 4)) + tx * 4]);
-                        av[i] = v.x; av[i + 1] = v.y; av[i + 2] = v.z; av[i + 3] = v.w;
+                        av[i / 2] = make_float2(v.x, v.y);
+                        av[i / 2 + 1] = make_float2(v.z, v.w);
                     }
 #pragma unroll
-                    for (int j = 0; j < TN; j++)
+                    for (int j = 0; j < TN; j++) {
+                        const float2 bb = make_float2(bv[j][kk], bv[j][kk]);
 #pragma unroll
-                        for (int i = 0; i < TM; i++) acc[j][i] = fmaf(av[i], bv[j][kk], acc[j][i]);
+                        for (int i = 0; i < TM / 2; i++) acc[j][i] = __ffma2_rn(av[i], bb, acc[j][i]);
+                    }
                 }
             }
             __syncthreads();
@@ -539,12 +544,13 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm_rt(size_t m, si
             for (int i = 0; i < TM; i += 4) {
                 float4 *p = reinterpret_cast<float4 *>(c + (i / 4) * (BM / (TM / 4)) + (size_t) j * ldc);
                 float4 o;
+                const float2 a01 = acc[j][i / 2], a23 = acc[j][i / 2 + 1];
                 if (beta == 0.f) {
-                    o = make_float4(alpha * acc[j][i], alpha * acc[j][i + 1], alpha * acc[j][i + 2], alpha * acc[j][i + 3]);
+                    o = make_float4(alpha * a01.x, alpha * a01.y, alpha * a23.x, alpha * a23.y);
                 } else {
                     const float4 old = *p;
-                    o = make_float4(alpha * acc[j][i] + beta * old.x, alpha * acc[j][i + 1] + beta * old.y,
-                                    alpha * acc[j][i + 2] + beta * old.z, alpha * acc[j][i + 3] + beta * old.w);
+                    o = make_float4(alpha * a01.x + beta * old.x, alpha * a01.y + beta * old.y, alpha * a23.x + beta * old.z,
+                                    alpha * a23.y + beta * old.w);
                 }
                 *p = o;
             }
@@ -565,12 +571,12 @@ bool try_sgemm_rt<float>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n
     const size_t cap = (size_t) ctx->sm_count * 8;
     if (m % 128 == 0 && n % 128 == 0) {
         const size_t tm = m / 128, tn = n / 128, total = tm * tn * batch;
-        k_sgemm_rt<128, 128, 8, 8><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+        k_sgemm_rt<128, 128, 8, 8, 2><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
         return true;
     }
     if (m % 64 == 0 && n % 64 == 0) {
         const size_t tm = m / 64, tn = n / 64, total = tm * tn * batch;
-        k_sgemm_rt<64, 64, 4, 8><<<(unsigned) (total < cap ? total : cap), 128, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+        k_sgemm_rt<64, 64, 8, 4, 1><<<(unsigned) (total < cap ? total : cap), 128, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
         return true;
     }
     return false;
