@@ -664,6 +664,108 @@ k_potrs_blk(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, si
 }
 
 // ------------------------------------------------------------------------------------------
+// potrs, 32 < n <= 64: k_potrs_pair64<T, DENSE>, a WARP per matrix, lane p owns rows p and p + 32 of L in registers
+// (the layout of k_potrf_pair<T, 64>), no CTA barrier. With the row-scaled factor Lb = D^-1 L:
+//   forward  Lb y = D^-1 b : 64 steps of one shuffle + two FMAs (column j of Lb is spread over the lanes' registers);
+//   backward Lb^T v = y, x = D^-1 v, by 32 x 32 blocks: the two diagonal blocks are transposed once through a padded
+//            shared tile so that lane p owns COLUMN p (31 steps of one shuffle + one FMA each); the coupling block
+//            Lb(32:64, 0:32)^T v_hi is 32 per-lane products reduced by a transpose-reduce butterfly (31 shuffles).
+// L is read exactly once (lower triangle). Rows / columns beyond n are an identity pad when !DENSE.
+// ------------------------------------------------------------------------------------------
+template<typename T, bool DENSE>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(int n_rt, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b,
+                                                                               size_t strideB, size_t batch) {
+    __shared__ T s_t[4][32][33];
+    const int n = DENSE ? 64 : n_rt;
+    const size_t ldl = DENSE ? (size_t) 64 : ldl_rt;
+    const int warp = threadIdx.x >> 5, p = threadIdx.x & 31;
+    const size_t nwarps = (size_t) gridDim.x * 4;
+    const size_t iters = (batch + nwarps - 1) / nwarps;
+    T (*tile)[33] = s_t[warp];
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * nwarps + (size_t) blockIdx.x * 4 + warp;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
+        const T *l_g = L + mat * strideL;
+        T *b_g = b + mat * strideB;
+        const bool lo_ok = DENSE || p < n, hi_ok = DENSE || p + 32 < n;
+        T lo[32], hi[64];
+#pragma unroll
+        for (int c = 0; c < 32; c++) lo[c] = (c <= p && lo_ok) ? l_g[p + c * ldl] : T(c == p ? 1 : 0);
+#pragma unroll
+        for (int c = 0; c < 64; c++) hi[c] = (c <= p + 32 && hi_ok) ? l_g[p + 32 + c * ldl] : T(c == p + 32 ? 1 : 0);
+        T xlo = lo_ok ? b_g[p] : T(0), xhi = hi_ok ? b_g[p + 32] : T(0);
+        T dlo = T(1), dhi = T(1);
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            if (c == p) dlo = lo[c];
+            if (c == p) dhi = hi[c + 32];
+        }
+        const T ilo = T(1) / dlo, ihi = T(1) / dhi;
+#pragma unroll
+        for (int c = 0; c < 32; c++) lo[c] = c < p ? lo[c] * ilo : T(0);          // strictly lower part of D^-1 L
+#pragma unroll
+        for (int c = 0; c < 64; c++) hi[c] = c < p + 32 ? hi[c] * ihi : T(0);
+        xlo *= ilo;
+        xhi *= ihi;
+        // forward
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const T yj = __shfl_sync(0xffffffffu, xlo, j);
+            xlo = fma(-lo[j], yj, xlo);
+            xhi = fma(-hi[j], yj, xhi);
+        }
+#pragma unroll
+        for (int j = 32; j < 63; j++) {
+            const T yj = __shfl_sync(0xffffffffu, xhi, j - 32);
+            xhi = fma(-hi[j], yj, xhi);
+        }
+        // backward, block 2: columns of Lb(32:64, 32:64)
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; c++) tile[p][c] = hi[32 + c];
+        __syncwarp();
+        {
+            T cb[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+#pragma unroll
+            for (int jj = 31; jj > 0; jj--) {
+                const T vj = __shfl_sync(0xffffffffu, xhi, jj);
+                xhi = fma(-cb[jj], vj, xhi);
+            }
+        }
+        // coupling: y_lo -= Lb(32:64, 0:32)^T v_hi
+        {
+            T pr[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) pr[c] = hi[c] * xhi;
+            TReduce<T, 32, 16>::run(pr, p);
+            xlo -= pr[0];
+        }
+        // backward, block 1: columns of Lb(0:32, 0:32)
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; c++) tile[p][c] = lo[c];
+        __syncwarp();
+        {
+            T cb[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+#pragma unroll
+            for (int jj = 31; jj > 0; jj--) {
+                const T vj = __shfl_sync(0xffffffffu, xlo, jj);
+                xlo = fma(-cb[jj], vj, xlo);
+            }
+        }
+        if (live) {
+            if (lo_ok) b_g[p] = xlo * ilo;
+            if (hi_ok) b_g[p + 32] = xhi * ihi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // potrs, any n: one CTA per matrix, rhs in shared memory, coalesced column sweeps of L
 // ------------------------------------------------------------------------------------------
 template<typename T>
@@ -798,6 +900,11 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
         }
 #undef GPUB_POTRS_LAUNCH
 #undef GPUB_POTRS_CASE
+    } else if (n <= 64) {
+        const size_t want = gpub_ceil_div(batch, (size_t) 4), cap = (size_t) ctx->sm_count * (sizeof(T) == 8 ? 2 : 4) * 2;
+        const unsigned grid = (unsigned) (want < cap ? want : cap);
+        if (n == 64 && ldl == 64) k_potrs_pair64<T, true><<<grid, 128, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
+        else k_potrs_pair64<T, false><<<grid, 128, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
     } else if (n <= 128) {
         const size_t cap = (size_t) ctx->sm_count * 8;
         const unsigned grid = (unsigned) (batch < cap ? batch : cap);
