@@ -358,14 +358,17 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 
 // TRB: the second operand is given transposed (B = Bt^T with Bt n x k column-major, ldb its leading dimension): the
 // panel then lands as [kk][col] like A's and its fragments are read with A's conflict-free pattern (P = N N^T).
-template<bool TRB>
+// DKT: depth of a K panel (16 or 32; 32 halves the number of CTA barriers per tile and needs dynamic shared memory)
+template<bool TRB, int DKT>
 __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
                                                     size_t tiles_n, size_t batch) {
     // As[buf][kk][row] (A panel, 16 x 64), Bs[buf][col][kk] (B panel stored k-contiguous per column)
-    __shared__ __align__(16) double As[2][DK][DLD];
-    __shared__ __align__(16) double Bs[2][TRB ? DK : 64][TRB ? DLD : DK + 4];
+    constexpr int BROWS = TRB ? DKT : 64, BLD = TRB ? DLD : DKT + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*As)[DKT][DLD] = reinterpret_cast<double (*)[DKT][DLD]>(smem_raw);
+    double (*Bs)[BROWS][BLD] = reinterpret_cast<double (*)[BROWS][BLD]>(smem_raw + sizeof(double) * 2 * DKT * DLD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32; // warp origin inside the tile
     const int g = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
@@ -382,41 +385,41 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
             for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         auto load_panel = [&](int buf, size_t k0) {
-            // A: 16 columns of 64 rows = 512 double2 ; 256 threads x 2
+            // A: DKT columns of 64 rows = 32 DKT double2 ; 256 threads x DKT / 8
 #pragma unroll
-            for (int l = 0; l < 2; l++) {
+            for (int l = 0; l < DKT / 8; l++) {
                 int e = threadIdx.x + l * 256;
                 int rr = (e & 31) * 2, kk = e >> 5;
                 cp_async16(&As[buf][kk][rr], a + rr + (k0 + kk) * lda);
             }
-            // B: 64 columns of 16 k = 512 double2
+            // B: 64 columns of DKT k = 32 DKT double2
 #pragma unroll
-            for (int l = 0; l < 2; l++) {
+            for (int l = 0; l < DKT / 8; l++) {
                 int e = threadIdx.x + l * 256;
                 if (TRB) {
                     int cc = (e & 31) * 2, kk = e >> 5;
                     cp_async16(&Bs[buf][kk][cc], bb + cc + (k0 + kk) * ldb);
                 } else {
-                    int kk = (e & 7) * 2, cc = e >> 3;
+                    int kk = (e % (DKT / 2)) * 2, cc = e / (DKT / 2);
                     cp_async16(&Bs[buf][cc][kk], bb + (k0 + kk) + (size_t) cc * ldb);
                 }
             }
             cp_async_commit();
         };
 
-        const size_t npan = k / DK;
+        const size_t npan = k / DKT;
         load_panel(0, 0);
         for (size_t p = 0; p < npan; p++) {
             const int buf = (int) (p & 1);
             if (p + 1 < npan) {
-                load_panel(buf ^ 1, (p + 1) * DK);
+                load_panel(buf ^ 1, (p + 1) * DKT);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
             __syncthreads();
 #pragma unroll
-            for (int k4 = 0; k4 < DK; k4 += 4) {
+            for (int k4 = 0; k4 < DKT; k4 += 4) {
                 double af[2], bf[4];
 #pragma unroll
                 for (int i = 0; i < 2; i++) af[i] = As[buf][k4 + q][wr + 8 * i + g]; // A(row g, k q)
@@ -996,8 +999,16 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
         const bool ok = (m % 64 == 0) && (n % 64 == 0) && (k % DK == 0) && k >= DK && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         ((((uintptr_t) A) | ((uintptr_t) B)) % 16 == 0) && (sA % 2 == 0) && (sB % 2 == 0);
         if (ok) {
-            k_gemm_dmma<false><<<grid, 256, 0, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
-                                                  ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+            if (false && k % 32 == 0) {   // measured: 32-deep panels are 2 % slower than 16-deep ones on 128^3 (profiles/r1e)
+                constexpr size_t smem32 = sizeof(double) * (2 * 32 * DLD + 2 * 64 * (32 + 4));
+                GPUB_CUDA(cudaFuncSetAttribute(k_gemm_dmma<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem32));
+                k_gemm_dmma<false, 32><<<grid, 256, smem32, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+                                                                      ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+            } else {
+                constexpr size_t smem16 = sizeof(double) * (2 * 16 * DLD + 2 * 64 * (16 + 4));
+                k_gemm_dmma<false, 16><<<grid, 256, smem16, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+                                                                      ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+            }
             done = true;
         }
     }
@@ -1030,7 +1041,8 @@ template<>
 bool try_aat_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *N, size_t sN, double *P, size_t sP, size_t batch) {
     if (n % 64 != 0 || (sN & 1) || (((uintptr_t) N) & 15u)) return false;
     const size_t tm = n / 64, total = tm * tm * batch, cap = (size_t) ctx->sm_count * 8;
-    k_gemm_dmma<true><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
+    constexpr size_t smemT = sizeof(double) * (2 * 16 * DLD + 2 * 16 * DLD);
+    k_gemm_dmma<true, 16><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
     return true;
 }
 
