@@ -672,6 +672,86 @@ k_potrs_blk(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, si
 //            Lb(32:64, 0:32)^T v_hi is 32 per-lane products reduced by a transpose-reduce butterfly (31 shuffles).
 // L is read exactly once (lower triangle). Rows / columns beyond n are an identity pad when !DENSE.
 // ------------------------------------------------------------------------------------------
+// Pieces shared by k_potrs_pair64 and k_potrs_quad128: a 64 x 64 lower-triangular block held by one warp as row pairs
+// (lane p: rows p and p + 32), already row-scaled to the strictly lower part of Lb = D^-1 L.
+template<typename T>
+__device__ __forceinline__ void pair64_load_scaled(const T *l_g, size_t ldl, int nloc, int p, T (&lo)[32], T (&hi)[64], T &ilo, T &ihi) {
+    // l_g points at the block's (0, 0) entry; rows >= nloc are an identity pad
+    const bool lo_ok = p < nloc, hi_ok = p + 32 < nloc;
+#pragma unroll
+    for (int c = 0; c < 32; c++) lo[c] = (c <= p && lo_ok) ? l_g[p + c * ldl] : T(c == p ? 1 : 0);
+#pragma unroll
+    for (int c = 0; c < 64; c++) hi[c] = (c <= p + 32 && hi_ok) ? l_g[p + 32 + c * ldl] : T(c == p + 32 ? 1 : 0);
+    T dlo = T(1), dhi = T(1);
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        if (c == p) dlo = lo[c];
+        if (c == p) dhi = hi[c + 32];
+    }
+    ilo = T(1) / dlo;
+    ihi = T(1) / dhi;
+#pragma unroll
+    for (int c = 0; c < 32; c++) lo[c] = c < p ? lo[c] * ilo : T(0);
+#pragma unroll
+    for (int c = 0; c < 64; c++) hi[c] = c < p + 32 ? hi[c] * ihi : T(0);
+}
+
+// Lb y = x (x already scaled by D^-1); on exit xlo, xhi hold y
+template<typename T>
+__device__ __forceinline__ void pair64_forward(const T (&lo)[32], const T (&hi)[64], T &xlo, T &xhi) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const T yj = __shfl_sync(0xffffffffu, xlo, j);
+        xlo = fma(-lo[j], yj, xlo);
+        xhi = fma(-hi[j], yj, xhi);
+    }
+#pragma unroll
+    for (int j = 32; j < 63; j++) {
+        const T yj = __shfl_sync(0xffffffffu, xhi, j - 32);
+        xhi = fma(-hi[j], yj, xhi);
+    }
+}
+
+// Lb^T v = x; on exit xlo, xhi hold v (the caller multiplies by D^-1). tile: the warp's [32][33] scratch
+template<typename T>
+__device__ __forceinline__ void pair64_backward(const T (&lo)[32], const T (&hi)[64], T &xlo, T &xhi, T (*tile)[33], int p) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) tile[p][c] = hi[32 + c];
+    __syncwarp();
+    {
+        T cb[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+#pragma unroll
+        for (int jj = 31; jj > 0; jj--) {
+            const T vj = __shfl_sync(0xffffffffu, xhi, jj);
+            xhi = fma(-cb[jj], vj, xhi);
+        }
+    }
+    {
+        T pr[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) pr[c] = hi[c] * xhi;
+        TReduce<T, 32, 16>::run(pr, p);
+        xlo -= pr[0];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) tile[p][c] = lo[c];
+    __syncwarp();
+    {
+        T cb[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+#pragma unroll
+        for (int jj = 31; jj > 0; jj--) {
+            const T vj = __shfl_sync(0xffffffffu, xlo, jj);
+            xlo = fma(-cb[jj], vj, xlo);
+        }
+    }
+}
+
 template<typename T, bool DENSE>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(int n_rt, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b,
                                                                                size_t strideB, size_t batch) {
@@ -681,87 +761,110 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(in
     const int warp = threadIdx.x >> 5, p = threadIdx.x & 31;
     const size_t nwarps = (size_t) gridDim.x * 4;
     const size_t iters = (batch + nwarps - 1) / nwarps;
-    T (*tile)[33] = s_t[warp];
     for (size_t it = 0; it < iters; it++) {
         size_t mat = it * nwarps + (size_t) blockIdx.x * 4 + warp;
         const bool live = mat < batch;
         if (!live) mat = batch - 1;
+        T *b_g = b + mat * strideB;
+        T lo[32], hi[64], ilo, ihi;
+        pair64_load_scaled<T>(L + mat * strideL, ldl, n, p, lo, hi, ilo, ihi);
+        T xlo = p < n ? b_g[p] * ilo : T(0), xhi = p + 32 < n ? b_g[p + 32] * ihi : T(0);
+        pair64_forward<T>(lo, hi, xlo, xhi);
+        pair64_backward<T>(lo, hi, xlo, xhi, s_t[warp], p);
+        if (live) {
+            if (p < n) b_g[p] = xlo * ilo;
+            if (p + 32 < n) b_g[p + 32] = xhi * ihi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// potrs, 64 < n <= 128: k_potrs_quad128<T>, one matrix per CTA of four warps, L = [L11 0; L21 L22] in 64 x 64 blocks:
+//   warp 0 holds L11 and warp 3 holds L22 as row pairs (pair64 pieces above), warps 1 and 2 hold the 64 rows of L21 (one full
+//   row of 64 entries per lane). Everything is row-scaled (Lb = D^-1 L) when loaded; L is read exactly once.
+//   forward : warp 0 solves block 1 -> warps 1, 2: rhs2 -= Lb21 y1 (a 64-term dot product per lane against the broadcast y1)
+//             -> warp 3 solves block 2 forward AND backward;
+//   backward: warps 1, 2: Lb21^T v2 (64 per-lane products, two 31-shuffle transpose-reduce butterflies) -> warp 0 finishes.
+// Five CTA barriers per matrix instead of the sixteen of k_potrs_blk<T, 4>, and no warp ever waits inside a 32-column block.
+// ------------------------------------------------------------------------------------------
+template<typename T>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 3) k_potrs_quad128(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b,
+                                                                                size_t strideB, size_t batch) {
+    __shared__ T s_t[2][32][33];
+    __shared__ __align__(16) T s_x[128];       // scaled right-hand side -> y -> v
+    __shared__ T s_part[2][64];
+    const int warp = threadIdx.x >> 5, p = threadIdx.x & 31;
+    const int n2 = n - 64;                      // rows of the second block (1..64)
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         const T *l_g = L + mat * strideL;
         T *b_g = b + mat * strideB;
-        const bool lo_ok = DENSE || p < n, hi_ok = DENSE || p + 32 < n;
-        T lo[32], hi[64];
-#pragma unroll
-        for (int c = 0; c < 32; c++) lo[c] = (c <= p && lo_ok) ? l_g[p + c * ldl] : T(c == p ? 1 : 0);
-#pragma unroll
-        for (int c = 0; c < 64; c++) hi[c] = (c <= p + 32 && hi_ok) ? l_g[p + 32 + c * ldl] : T(c == p + 32 ? 1 : 0);
-        T xlo = lo_ok ? b_g[p] : T(0), xhi = hi_ok ? b_g[p + 32] : T(0);
-        T dlo = T(1), dhi = T(1);
-#pragma unroll
-        for (int c = 0; c < 32; c++) {
-            if (c == p) dlo = lo[c];
-            if (c == p) dhi = hi[c + 32];
-        }
-        const T ilo = T(1) / dlo, ihi = T(1) / dhi;
-#pragma unroll
-        for (int c = 0; c < 32; c++) lo[c] = c < p ? lo[c] * ilo : T(0);          // strictly lower part of D^-1 L
-#pragma unroll
-        for (int c = 0; c < 64; c++) hi[c] = c < p + 32 ? hi[c] * ihi : T(0);
-        xlo *= ilo;
-        xhi *= ihi;
-        // forward
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const T yj = __shfl_sync(0xffffffffu, xlo, j);
-            xlo = fma(-lo[j], yj, xlo);
-            xhi = fma(-hi[j], yj, xhi);
-        }
-#pragma unroll
-        for (int j = 32; j < 63; j++) {
-            const T yj = __shfl_sync(0xffffffffu, xhi, j - 32);
-            xhi = fma(-hi[j], yj, xhi);
-        }
-        // backward, block 2: columns of Lb(32:64, 32:64)
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 32; c++) tile[p][c] = hi[32 + c];
-        __syncwarp();
-        {
-            T cb[32];
-#pragma unroll
-            for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
-#pragma unroll
-            for (int jj = 31; jj > 0; jj--) {
-                const T vj = __shfl_sync(0xffffffffu, xhi, jj);
-                xhi = fma(-cb[jj], vj, xhi);
+        if (warp == 0 || warp == 3) {
+            const int o = warp == 0 ? 0 : 64, nloc = warp == 0 ? 64 : n2;
+            T lo[32], hi[64], ilo, ihi;
+            pair64_load_scaled<T>(l_g + o + (size_t) o * ldl, ldl, nloc, p, lo, hi, ilo, ihi);
+            T xlo = p < nloc ? b_g[o + p] * ilo : T(0), xhi = p + 32 < nloc ? b_g[o + p + 32] * ihi : T(0);
+            if (warp == 0) {
+                pair64_forward<T>(lo, hi, xlo, xhi);
+                s_x[p] = xlo;
+                s_x[p + 32] = xhi;
+                __syncthreads();               // (1) y1 published
+                __syncthreads();               // (2) warps 1, 2 have updated the second right-hand side
+                __syncthreads();               // (3) v2 published
+                __syncthreads();               // (4) coupling partials published
+                xlo -= s_part[0][p] + s_part[1][p];
+                xhi -= s_part[0][p + 32] + s_part[1][p + 32];
+                pair64_backward<T>(lo, hi, xlo, xhi, s_t[0], p);
+                b_g[p] = xlo * ilo;
+                b_g[p + 32] = xhi * ihi;
+            } else {
+                s_x[64 + p] = xlo;             // scaled rhs of block 2, updated by warps 1, 2 after barrier (1)
+                s_x[96 + p] = xhi;
+                __syncthreads();               // (1)
+                __syncthreads();               // (2)
+                xlo = s_x[64 + p];
+                xhi = s_x[96 + p];
+                pair64_forward<T>(lo, hi, xlo, xhi);
+                pair64_backward<T>(lo, hi, xlo, xhi, s_t[1], p);
+                s_x[64 + p] = xlo;             // v2
+                s_x[96 + p] = xhi;
+                if (p < nloc) b_g[64 + p] = xlo * ilo;
+                if (p + 32 < nloc) b_g[96 + p] = xhi * ihi;
+                __syncthreads();               // (3)
+                __syncthreads();               // (4)
             }
-        }
-        // coupling: y_lo -= Lb(32:64, 0:32)^T v_hi
-        {
+        } else {
+            // one row of L21 per lane: row 64 + 32 (warp - 1) + p, scaled by the reciprocal diagonal of ITS row
+            const int rloc = 32 * (warp - 1) + p, row = 64 + rloc;
+            const bool ok = rloc < n2;
+            T r[64];
+#pragma unroll
+            for (int c = 0; c < 64; c++) r[c] = ok ? l_g[row + c * ldl] : T(0);
+            const T idg = ok ? T(1) / l_g[row + (size_t) row * ldl] : T(1);
+#pragma unroll
+            for (int c = 0; c < 64; c++) r[c] *= idg;
+            __syncthreads();                   // (1) y1 published
+            T t0 = 0, t1 = 0;
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+                t0 = fma(r[c], s_x[c], t0);
+                t1 = fma(r[c + 1], s_x[c + 1], t1);
+            }
+            s_x[row] -= t0 + t1;
+            __syncthreads();                   // (2)
+            __syncthreads();                   // (3) v2 published
+            const T v = s_x[row];
             T pr[32];
 #pragma unroll
-            for (int c = 0; c < 32; c++) pr[c] = hi[c] * xhi;
+            for (int c = 0; c < 32; c++) pr[c] = r[c] * v;
             TReduce<T, 32, 16>::run(pr, p);
-            xlo -= pr[0];
-        }
-        // backward, block 1: columns of Lb(0:32, 0:32)
-        __syncwarp();
+            s_part[warp - 1][p] = pr[0];
 #pragma unroll
-        for (int c = 0; c < 32; c++) tile[p][c] = lo[c];
-        __syncwarp();
-        {
-            T cb[32];
-#pragma unroll
-            for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
-#pragma unroll
-            for (int jj = 31; jj > 0; jj--) {
-                const T vj = __shfl_sync(0xffffffffu, xlo, jj);
-                xlo = fma(-cb[jj], vj, xlo);
-            }
+            for (int c = 0; c < 32; c++) pr[c] = r[32 + c] * v;
+            TReduce<T, 32, 16>::run(pr, p);
+            s_part[warp - 1][p + 32] = pr[0];
+            __syncthreads();                   // (4)
         }
-        if (live) {
-            if (lo_ok) b_g[p] = xlo * ilo;
-            if (hi_ok) b_g[p + 32] = xhi * ihi;
-        }
+        __syncthreads();                       // (5) the shared vectors are free for the next matrix
     }
 }
 
@@ -908,6 +1011,11 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
     } else if (n <= 128) {
         const size_t cap = (size_t) ctx->sm_count * 8;
         const unsigned grid = (unsigned) (batch < cap ? batch : cap);
+#ifndef GPUB_POTRS_BLK128
+        k_potrs_quad128<T><<<grid, 128, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
+        GPUB_LAUNCH_CHECK();
+        return GPUB_OK;
+#endif
         if (n <= 64) k_potrs_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
         else if (n <= 96) k_potrs_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
         else k_potrs_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);

@@ -70,8 +70,15 @@ __global__ void k_init_u(int m, int n, const T *__restrict__ Ur, size_t sUr, T *
 // Columns with a negligible norm (rank deficiency) are replaced by an orthonormal completion so Vt is always
 // an orthogonal matrix, which Nullspace relies on.
 // ------------------------------------------------------------------------------------------
-constexpr int JT = 512; // threads per CTA
-constexpr int JP = 4;   // pairs a warp rotates at once
+#ifndef GPUB_JACOBI_THREADS
+#define GPUB_JACOBI_THREADS 512
+#endif
+#ifndef GPUB_JACOBI_PAIRS
+#define GPUB_JACOBI_PAIRS 4
+#endif
+constexpr int JT = GPUB_JACOBI_THREADS; // threads per CTA
+constexpr int JP = GPUB_JACOBI_PAIRS;   // pairs a warp rotates at once (4 or 2)
+constexpr int JRP = JP == 4 ? 16 : 8;   // values in the transpose-reduce (3 per pair, padded to a power of two)
 
 template<typename T> struct JacobiEps;
 template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; };
@@ -147,9 +154,9 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
                     int pp[JP], qq[JP];
                     unsigned vmask = 0;
                     T cu[JP][JE], cv[JP][JE];
-                    T red[16];
+                    T red[JRP];
 #pragma unroll
-                    for (int e = 0; e < 16; e++) red[e] = T(0);
+                    for (int e = 0; e < JRP; e++) red[e] = T(0);
 #pragma unroll
                     for (int u = 0; u < JP; u++) {
                         const int i = base + u * NW;
@@ -175,16 +182,17 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
                         }
                         red[3 * u] = aa; red[3 * u + 1] = bb; red[3 * u + 2] = cc;
                     }
-                    TReduce<T, 16, 16>::run(red, lane);          // lane l now holds the total of value l >> 1
+                    TReduce<T, JRP, 16>::run(red, lane);          // lane l now holds the total of value l / (32 / JRP)
                     const T tot = red[0];
                     // lane u (< JP) gathers the three sums of pair u and computes ITS rotation: the parameters of the JP pairs
                     // cost one instruction stream instead of JP (rsqrt / rcp seeds + Newton steps, no sqrt / divide slow paths)
-                    const int src = 6 * (lane & 3);
-                    const T aa = __shfl_sync(0xffffffffu, tot, src), bb = __shfl_sync(0xffffffffu, tot, src + 2),
-                            cc = __shfl_sync(0xffffffffu, tot, src + 4);
+                    constexpr int HS = 32 / JRP;                 // lanes per value
+                    const int src = 3 * HS * (lane % JP);
+                    const T aa = __shfl_sync(0xffffffffu, tot, src), bb = __shfl_sync(0xffffffffu, tot, src + HS),
+                            cc = __shfl_sync(0xffffffffu, tot, src + 2 * HS);
                     T cs = T(1), sn = T(0);
                     bool rot = false;
-                    if (((vmask >> (lane & 3)) & 1u) && cc != T(0) && cc * cc > tol2 * (aa * bb)) {
+                    if (((vmask >> (lane % JP)) & 1u) && cc != T(0) && cc * cc > tol2 * (aa * bb)) {
                         const T zeta = (bb - aa) * jac_rcp<T>(T(2) * cc);
                         const T az = fabs(zeta);
                         T t;
