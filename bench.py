@@ -56,30 +56,88 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line). The timed region of this
+    bench is ~60 ms, shorter than nvidia-smi's fastest loop can resolve reliably, so NVML is polled in-process every 2 ms
+    (same counters nvidia-smi prints); `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, uuid: str | None = None):
         self.index = index
+        self.uuid = uuid
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, max_mhz, power_w, reasons bitmask) from NVML
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = 0
+                self.samples.append((sm, self.max_mhz, pw, rs))
+            except Exception:
+                break
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            n = self.nvml
+            names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+            reasons = set()
+            for _, _, _, rs in self.samples:
+                for name, attr, dflt in names:
+                    if rs & int(getattr(n, attr, dflt)):
+                        reasons.add(name)
+            sm = [x[0] for x in self.samples]
+            pw = [x[2] for x in self.samples if x[2] == x[2]]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz if sm else None,
+                    "power_w_max": max(pw) if pw else None, "samples": len(sm), "source": "nvml, 2 ms polling during the timed region",
+                    "reasons": sorted(reasons)}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,7 +158,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvidia-smi -lms 20", "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -207,7 +265,7 @@ def main():
     assert int(info.abs().max()) == 0, "factorisation reported a non-SPD matrix on synthetic SPD input"
 
     # ---- timed region: exactly K steps ------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, str(torch.cuda.get_device_properties(local_rank).uuid))
     if use_dist:
         dist.barrier()
     torch.cuda.synchronize()
