@@ -30,7 +30,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(REPO / "include"), "-I", str(CSRC)]
 # per-file extra flags: the LAPACK-faithful SVD core must round exactly like its host build
 EXTRA = {"svd.cu": ["--fmad=false"]}
-SOURCES = ["ctx.cu", "blas1.cu", "gemm.cu", "chol.cu", "qr.cu", "svd.cu"]
+SOURCES = ["ctx.cu", "blas1.cu", "gemm.cu", "chol.cu", "qr.cu", "svd.cu", "multi.cu"]
 
 
 def nvcc() -> str:
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
     if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs):
-        cmd = [nvcc(), *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc(), *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -56,7 +56,8 @@ _TYPED = {
 #: every symbol include/gputils_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = (
     ["gpub_version", "gpub_ctx_get", "gpub_ctx_ensure_streams", "gpub_ctx_num_streams", "gpub_ctx_stream",
-     "gpub_ctx_bind_stream", "gpub_ctx_sync", "gpub_ctx_sync_all", "gpub_ctx_release", "gpub_ctx_device", "gpub_ctx_sm_count",
+     "gpub_ctx_bind_stream", "gpub_ctx_sync", "gpub_ctx_sync_all", "gpub_ctx_release", "gpub_ctx_release_all", "gpub_ctx_device", "gpub_ctx_sm_count",
+     "gpub_multi_device_count", "gpub_multi_enable_peer_access", "gpub_multi_nccl_version", "gpub_multi_allgather", "gpub_multi_release",
      "gpub_fill_ptr_table", "gpub_gesvd_batched_worksize_f64", "gpub_gesvd_batched_worksize_f32"]
     + [f"gpub_{n}_{s}" for n in _TYPED for s in ("f64", "f32")]
 )
@@ -87,6 +88,10 @@ def load() -> C.CDLL:
     lib.gpub_ctx_sync_all.argtypes = [_vp]
     lib.gpub_ctx_release.argtypes = [_vp]
     lib.gpub_ctx_device.argtypes = [_vp]
+    lib.gpub_multi_device_count.argtypes = [C.POINTER(_int)]
+    lib.gpub_multi_enable_peer_access.argtypes = [C.POINTER(_int), _int, C.POINTER(_int)]
+    lib.gpub_multi_nccl_version.argtypes = [C.POINTER(_int)]
+    lib.gpub_multi_allgather.argtypes = [C.POINTER(_vp), _int, _int, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), _int, C.POINTER(_int)]
     lib.gpub_ctx_sm_count.argtypes = [_vp]
     lib.gpub_fill_ptr_table.argtypes = [_vp, _int, _vp, _sz, _sz, _vp]
     for suf in ("f64", "f32"):

@@ -166,6 +166,20 @@ int gpub_ctx_release(gpub_ctx_t ctx) {
     return first_err;
 }
 
+int gpub_ctx_release_all(void) {
+    std::vector<gpub_ctx_t> all;
+    {
+        std::lock_guard<std::mutex> lock(g_registry_mu);
+        for (auto &kv: g_registry) all.push_back(kv.second.get());
+    }
+    int first_err = GPUB_OK;
+    for (gpub_ctx_t c: all) {
+        int e = gpub_ctx_release(c);
+        if (e != GPUB_OK && first_err == GPUB_OK) first_err = e;
+    }
+    return first_err;
+}
+
 int gpub_ctx_device(gpub_ctx_t ctx) { return ctx ? ctx->device : -1; }
 
 int gpub_ctx_sm_count(gpub_ctx_t ctx) { return ctx ? ctx->sm_count : 0; }

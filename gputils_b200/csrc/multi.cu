@@ -216,6 +216,7 @@ int gpub_multi_allgather(const gpub_ctx_t *ctxs, int n, int sidx, const void *co
 
 int gpub_multi_release(void) {
     std::lock_guard<std::mutex> lock(g_multi_mu);
+    if (g_comms.empty()) return GPUB_OK;
     NcclApi &api = nccl_api();
     for (auto &kv: g_comms)
         for (ncclComm_t c: kv.second)

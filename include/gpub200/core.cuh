@@ -153,16 +153,16 @@ public:
 
 private:
     explicit Session(size_t numStreams) : m_numStreams(numStreams == 0 ? 1 : numStreams) {
-        int device = 0;
-        gpuErrChk(cudaGetDevice(&device));
-        gpuErrChk(gpub_ctx_get(device, &m_ctx));
+        gpuErrChk(cudaGetDevice(&m_device));
+        gpuErrChk(gpub_ctx_get(m_device, &m_ctx));
         gpuErrChk(gpub_ctx_ensure_streams(m_ctx, static_cast<int>(m_numStreams)));
     }
 
     ~Session() {
         /* like the reference's destructor (tensor.cuh:168-173), which destroys its handles and streams:
          * hands the streams and the per-stream scratch back, so leak checkers see a clean exit */
-        if (m_ctx) gpub_ctx_release(m_ctx);
+        gpub_multi_release();   /* NCCL communicators of sharded tensors, if any were made */
+        gpub_ctx_release_all(); /* this device's context and those sharded tensors created on other devices */
 #ifdef GPUTILS_B200_ENABLE_CUBLAS_HANDLES
         for (auto &h: m_cublasHandles) if (h) cublasDestroy(h);
         for (auto &h: m_cusolverHandles) if (h) cusolverDnDestroy(h);
@@ -170,6 +170,7 @@ private:
     }
 
     gpub_ctx_t m_ctx = nullptr;
+    int m_device = 0;
     size_t m_bytesAllocated = 0;
     size_t m_numStreams = 1;
 #ifdef GPUTILS_B200_ENABLE_CUBLAS_HANDLES
@@ -189,6 +190,29 @@ public:
     cudaStream_t stream(size_t idx = 0) const {
         void *s = nullptr;
         gpuErrChk(gpub_ctx_stream(m_ctx, static_cast<int>(idx), &s));
+        return static_cast<cudaStream_t>(s);
+    }
+
+    /** Device the Session was created on (the current device at first use, as in the reference). */
+    int device() const { return m_device; }
+
+    /**
+     * Stream context of the CURRENT device (additive API). Equal to context() in single-GPU programs; sharded tensors
+     * (gpub200/sharded.cuh) make another device current around their launches and get that device's context.
+     */
+    gpub_ctx_t contextOfCurrentDevice() const {
+        int device = 0;
+        gpuErrChk(cudaGetDevice(&device));
+        if (device == m_device) return m_ctx;
+        gpub_ctx_t c = nullptr;
+        gpuErrChk(gpub_ctx_get(device, &c));
+        return c;
+    }
+
+    /** Raw CUDA stream behind stream index idx of the current device's context (additive API). */
+    cudaStream_t streamOfCurrentDevice(size_t idx = 0) const {
+        void *s = nullptr;
+        gpuErrChk(gpub_ctx_stream(contextOfCurrentDevice(), static_cast<int>(idx), &s));
         return static_cast<cudaStream_t>(s);
     }
 
@@ -244,7 +268,7 @@ public:
 
 namespace gpub200 {
 /* Type dispatch from T to the _f32 / _f64 entry points of the C ABI. */
-inline gpub_ctx_t ctx() { return Session::getInstance().context(); }
+inline gpub_ctx_t ctx() { return Session::getInstance().contextOfCurrentDevice(); }
 
 template<typename T> struct Abi;
 

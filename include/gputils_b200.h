@@ -60,6 +60,8 @@ int gpub_ctx_sync_all(gpub_ctx_t ctx);
 /* ref: tensor.cuh:168-173 (~Session destroys its handles): synchronise, then free the streams this context
  * owns and the per-stream scratch. The context stays valid; slots are recreated lazily if used again. */
 int gpub_ctx_release(gpub_ctx_t ctx);
+/* the same for every context created so far (one per device used) */
+int gpub_ctx_release_all(void);
 int gpub_ctx_device(gpub_ctx_t ctx);
 int gpub_ctx_sm_count(gpub_ctx_t ctx);
 
@@ -210,6 +212,27 @@ int gpub_fill_spd_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, double *A, siz
                               uint64_t seed, size_t batch);
 int gpub_fill_spd_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, float *A, size_t strideA, float shift,
                               uint64_t seed, size_t batch);
+
+/* ---- multi-GPU: the mats axis sharded over the GPUs of one box ---
+ * The reference binds one device (Session, tensor.cuh:133-247) and has no multi-GPU path; these are additive.
+ * Batched ops shard embarrassingly: each device runs the launchers above on its own block of matrices with its own
+ * context, so there is NO collective on the data path. The entry points below only make the devices NVLink peers and
+ * all-gather result shards (device g contributes bytes[g] bytes from send[g]; every recv[g] receives the concatenation
+ * in device order). Asynchronous on stream `sidx` of each context.
+ *   transport: GPUB_GATHER_AUTO -> NCCL when it can be loaded and the devices are distinct, else peer copies;
+ *              GPUB_GATHER_NCCL -> ncclAllGather (equal shards) / grouped ncclBroadcast (ragged), GPUB_ENOTSUP if unavailable;
+ *              GPUB_GATHER_P2P  -> cudaMemcpyPeerAsync pulls over NVLink (also serves a device listed twice). */
+#define GPUB_GATHER_AUTO 0
+#define GPUB_GATHER_NCCL 1
+#define GPUB_GATHER_P2P 2
+int gpub_multi_device_count(int *count);
+int gpub_multi_enable_peer_access(const int *devices, int n, int *n_pairs_enabled);
+/* NCCL version code (e.g. 22809) of the library found with dlopen, 0 if none */
+int gpub_multi_nccl_version(int *version);
+int gpub_multi_allgather(const gpub_ctx_t *ctxs, int n, int sidx, const void *const *send, const size_t *bytes,
+                         void *const *recv, int transport, int *transport_used);
+/* destroys the cached NCCL communicators */
+int gpub_multi_release(void);
 
 #ifdef __cplusplus
 }

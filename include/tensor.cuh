@@ -15,5 +15,6 @@
 #include "gpub200/core.cuh"
 #include "gpub200/dtensor.cuh"
 #include "gpub200/factorisers.cuh"
+#include "gpub200/sharded.cuh" /* additive: mats axis sharded over the GPUs of one box */
 
 #endif /* TENSOR_CUH */
