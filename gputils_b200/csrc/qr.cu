@@ -1141,26 +1141,81 @@ __device__ __forceinline__ void gels_cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 
-// The systems of the NEXT iteration are copied global -> shared with cp.async while the current ones are factorised
-// (each lane copies exactly the 16-byte pieces it will read itself, so no cross-lane synchronisation is needed; pieces
-// are laid out [column][piece][lane] so the LDS.128 are bank-conflict free), and column j is stored as soon as step j
-// has finished it: neither the load latency nor the 34 back-to-back STG.128 sit on the critical path any more.
-template<int M, int N, int LPM>
+// Row ownership (GPUB_GELS_ROWMAP = 1): lane l of a group owns the 4-row pieces {v * 4 LPM + 4 l .. + 3}, v = 0 .. RPL/4 - 1,
+// so the LPM lanes of a group touch one contiguous 16 LPM-byte run per 128-bit access (a full 128-byte line for LPM = 8) instead of
+// every other 16 bytes of a 32 LPM-byte run: half the L2 requests for the same data, on loads and on stores.
+// Staging (TMA = true, dense batches): the WG = 32 / LPM systems of a warp are contiguous in global memory, so ONE lane moves
+// them with two bulk copies (cp.async.bulk, SASS UBLKCP: [A of WG systems], [b of WG systems]) into the warp's shared-memory
+// slot, completion counted on the warp's mbarrier. The copy of iteration it + 1 is issued as soon as the lanes have pulled
+// iteration it into registers, so the HBM latency of the next systems hides behind the factorisation of the current ones
+// (ncu before: 22 % of the warp stalls were the long-scoreboard wait on the 34 LDG.128 at the top of every iteration).
+// GPUB_GELS_STAGE = 1 keeps the older per-lane cp.async staging for comparison. Column j is stored as soon as step j has
+// finished it, so the 34 STG.128 are not back to back at the end either.
+#ifndef GPUB_GELS_ROWMAP
+#define GPUB_GELS_ROWMAP 1
+#endif
+#ifndef GPUB_GELS_TMA
+#define GPUB_GELS_TMA 1
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GELS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GELS_DONE_%=;\n\t"
+        "bra GELS_WAIT_%=;\n\t"
+        "GELS_DONE_%=:\n\t}" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned) __cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+
+template<int M, int N, int LPM, bool TMA>
 __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_t sA, float *b, size_t sB, int *info, size_t batch) {
     constexpr int RPL = M / LPM;           // rows per lane
     constexpr int NP = RPL / 2;            // float2 pairs per lane per column
     constexpr int NV = RPL / 4;            // 128-bit accesses per lane per column
     static_assert(RPL % 4 == 0, "rows per lane must be a multiple of 4");
     constexpr int MPC = 128 / LPM;
+    constexpr int WG = 32 / LPM;           // systems per warp
     constexpr int SYS4 = (N + 1) * (M / 4); // float4 per system [A | b]
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw) + (size_t) (threadIdx.x / LPM) * SYS4;   // this group's system
+    constexpr int PS = GPUB_GELS_ROWMAP ? 4 * LPM : 4;          // rows between consecutive pieces of a lane
+    constexpr int PS4 = GPUB_GELS_ROWMAP ? LPM : 1;             // the same in float4 units
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int l = threadIdx.x % LPM;
+    const int g = (threadIdx.x & 31) / LPM;
+    const int warp = threadIdx.x >> 5;
     const int gl = (threadIdx.x & 31) - l;
-    const int row0 = l * RPL;
+    const int row0 = GPUB_GELS_ROWMAP ? 4 * l : l * RPL;        // first row of piece 0
+    const int l4 = GPUB_GELS_ROWMAP ? l : l * NV;               // float4 index of piece 0 inside a column
+    // row of pair t: piece t / 2, pair t % 2 inside the piece
+    auto row_of = [&](int t) { return row0 + (t >> 1) * PS + 2 * (t & 1); };
+    // where the diagonal entry (j, j) lives
+    auto diag_lane = [](int j) { return GPUB_GELS_ROWMAP ? (j % (4 * LPM)) / 4 : j / RPL; };
+    auto diag_pair = [](int j) { return GPUB_GELS_ROWMAP ? 2 * (j / (4 * LPM)) + (j % 4) / 2 : (j % RPL) / 2; };
     const size_t ngroups = (size_t) gridDim.x * MPC;
     const size_t iters = (batch + ngroups - 1) / ngroups;
 
+    // ---- staging ----
+    // TMA: per warp [WG systems of A][WG right-hand sides], then the 4 mbarriers of the CTA
+    float4 *wstage = reinterpret_cast<float4 *>(smem_raw) + (size_t) warp * WG * SYS4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t) 4 * WG * SYS4 * sizeof(float4));
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw) + (size_t) (threadIdx.x / LPM) * SYS4;   // cp.async staging: this group's system
+    auto tma_issue = [&](size_t it_) {       // one lane of the warp
+        const size_t m0 = it_ * ngroups + (size_t) blockIdx.x * MPC + (size_t) warp * WG;
+        if (m0 >= batch) return;
+        const unsigned nlive = (unsigned) (batch - m0 < (size_t) WG ? batch - m0 : (size_t) WG);
+        mbar_expect_tx(&bars[warp], nlive * (unsigned) (SYS4 * sizeof(float4)));
+        bulk_g2s(wstage, A + m0 * (size_t) (M * N), nlive * (unsigned) (M * N * sizeof(float)), &bars[warp]);
+        bulk_g2s(wstage + WG * (M * N / 4), b + m0 * (size_t) M, nlive * (unsigned) (M * sizeof(float)), &bars[warp]);
+    };
     auto prefetch = [&](size_t it_) {
         size_t mat = it_ * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
         if (mat >= batch) mat = batch - 1;
@@ -1168,15 +1223,25 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
 #pragma unroll
         for (int c = 0; c <= N; c++)
 #pragma unroll
-            for (int v = 0; v < NV; v++) gels_cp_async16(&stage[c * (M / 4) + v * LPM + l], (c < N ? a_n + (size_t) c * M : b_n) + 4 * v);
+            for (int v = 0; v < NV; v++) gels_cp_async16(&stage[c * (M / 4) + v * LPM + l], (c < N ? a_n + (size_t) c * M : b_n) + v * PS);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) mbar_init(&bars[w], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && iters > 0) tma_issue(0);
+    } else {
 #if GPUB_GELS_STAGE
-    if (iters > 0) prefetch(0);
+        if (iters > 0) prefetch(0);
 #else
-    (void) stage; (void) prefetch;
+        (void) stage; (void) prefetch;
 #endif
+    }
     for (size_t it = 0; it < iters; it++) {
         size_t mat = it * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
         const bool live = mat < batch;
@@ -1184,34 +1249,44 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
         float *a_g = A + mat * sA + row0;
         float *b_g = b + mat * sB + row0;
         float2 a[N + 1][NP];
-#if GPUB_GELS_STAGE
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
+        if constexpr (TMA) {
+            const size_t m0 = it * ngroups + (size_t) blockIdx.x * MPC + (size_t) warp * WG;
+            if (m0 < batch) mbar_wait(&bars[warp], (unsigned) (it & 1));
 #pragma unroll
-        for (int c = 0; c <= N; c++) {
+            for (int c = 0; c <= N; c++) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-#if GPUB_GELS_STAGE
-                const float4 x = stage[c * (M / 4) + v * LPM + l];
-#else
-                const float4 x = reinterpret_cast<const float4 *>(c < N ? a_g + (size_t) c * M : b_g)[v];
-#endif
-                a[c][2 * v] = make_float2(x.x, x.y);
-                a[c][2 * v + 1] = make_float2(x.z, x.w);
+                for (int v = 0; v < NV; v++) {
+                    const float4 x = c < N ? wstage[g * (M * N / 4) + c * (M / 4) + l4 + v * PS4]
+                                           : wstage[WG * (M * N / 4) + g * (M / 4) + l4 + v * PS4];
+                    a[c][2 * v] = make_float2(x.x, x.y);
+                    a[c][2 * v + 1] = make_float2(x.z, x.w);
+                }
             }
-        }
+            // every lane has pulled its pieces: order the generic-proxy reads before the async-proxy refill of the slot
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0 && it + 1 < iters) tma_issue(it + 1);
+        } else {
 #if GPUB_GELS_STAGE
-        if (it + 1 < iters) prefetch(it + 1);   // the lane has consumed its own pieces: the slot can be refilled
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
-#if GPUB_GELS_L2PF
-        if (it + 1 < iters) {                   // pull the next system of this lane group into L2 (34 lines of 128 bytes)
-            size_t nm = (it + 1) * ngroups + (size_t) blockIdx.x * MPC + threadIdx.x / LPM;
-            if (nm >= batch) nm = batch - 1;
-            const char *pa = reinterpret_cast<const char *>(A + nm * sA), *pb = reinterpret_cast<const char *>(b + nm * sB);
-            for (int ln = l; ln < (N * M * 4) / 128; ln += LPM) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 128 * ln));
-            if (l < (M * 4) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + 128 * l));
+#pragma unroll
+            for (int c = 0; c <= N; c++) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+#if GPUB_GELS_STAGE
+                    const float4 x = stage[c * (M / 4) + v * LPM + l];
+#else
+                    const float4 x = *reinterpret_cast<const float4 *>((c < N ? a_g + (size_t) c * M : b_g) + v * PS);
+#endif
+                    a[c][2 * v] = make_float2(x.x, x.y);
+                    a[c][2 * v + 1] = make_float2(x.z, x.w);
+                }
+            }
+#if GPUB_GELS_STAGE
+            if (it + 1 < iters) prefetch(it + 1);   // the lane has consumed its own pieces: the slot can be refilled
+#endif
         }
-#endif
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -1219,12 +1294,12 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
             float2 part = make_float2(0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < NP; t++) {
-                const float2 x = make_float2(row0 + 2 * t > j ? a[j][t].x : 0.f, row0 + 2 * t + 1 > j ? a[j][t].y : 0.f);
+                const float2 x = make_float2(row_of(t) > j ? a[j][t].x : 0.f, row_of(t) + 1 > j ? a[j][t].y : 0.f);
                 part = __ffma2_rn(x, x, part);
             }
             const float xnorm2 = group_sum<float, LPM>(part.x + part.y);
-            const float ajj = ((j % RPL) & 1) ? a[j][(j % RPL) / 2].y : a[j][(j % RPL) / 2].x;
-            const float alpha = __shfl_sync(0xffffffffu, ajj, gl + j / RPL);
+            const float ajj = (j & 1) ? a[j][diag_pair(j)].y : a[j][diag_pair(j)].x;
+            const float alpha = __shfl_sync(0xffffffffu, ajj, gl + diag_lane(j));
             float tau = 0.f, scale = 0.f, beta = alpha;
             if (xnorm2 != 0.f) {
                 const float ss = fmaf(alpha, alpha, xnorm2);
@@ -1243,14 +1318,14 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
             float2 v[NP];
 #pragma unroll
             for (int t = 0; t < NP; t++) {
-                const int r0 = row0 + 2 * t, r1 = r0 + 1;
+                const int r0 = row_of(t), r1 = r0 + 1;
                 v[t] = make_float2(r0 > j ? a[j][t].x * scale : (r0 == j ? 1.f : 0.f), r1 > j ? a[j][t].y * scale : (r1 == j ? 1.f : 0.f));
                 a[j][t] = make_float2(r0 > j ? v[t].x : (r0 == j ? beta : a[j][t].x), r1 > j ? v[t].y : (r1 == j ? beta : a[j][t].y));
             }
             if (GPUB_GELS_EARLY && live) {                     // column j is final
-                float4 *dst = reinterpret_cast<float4 *>(a_g + (size_t) j * M);
 #pragma unroll
-                for (int vv = 0; vv < NV; vv++) dst[vv] = make_float4(a[j][2 * vv].x, a[j][2 * vv].y, a[j][2 * vv + 1].x, a[j][2 * vv + 1].y);
+                for (int vv = 0; vv < NV; vv++)
+                    *reinterpret_cast<float4 *>(a_g + (size_t) j * M + vv * PS) = make_float4(a[j][2 * vv].x, a[j][2 * vv].y, a[j][2 * vv + 1].x, a[j][2 * vv + 1].y);
             }
             float w[N + 1];
 #pragma unroll
@@ -1269,19 +1344,20 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
                 for (int t = 0; t < NP; t++) a[c][t] = __ffma2_rn(nw, v[t], a[c][t]);
             }
         }
-        // back substitution on R: row j lives in lane j / RPL, slot j % RPL
+        // back substitution on R: row j lives in lane diag_lane(j), pair diag_pair(j); only pairs holding rows < N take part
+        constexpr int NPB = (GPUB_GELS_ROWMAP && N <= 4 * LPM) ? (NP < 2 ? NP : 2) : NP;
 #pragma unroll
         for (int j = N - 1; j >= 0; j--) {
-            const float bj = ((j % RPL) & 1) ? a[N][(j % RPL) / 2].y : a[N][(j % RPL) / 2].x;
-            const float rjj = ((j % RPL) & 1) ? a[j][(j % RPL) / 2].y : a[j][(j % RPL) / 2].x;
-            const float num = __shfl_sync(0xffffffffu, bj, gl + j / RPL), den = __shfl_sync(0xffffffffu, rjj, gl + j / RPL);
+            const float bj = (j & 1) ? a[N][diag_pair(j)].y : a[N][diag_pair(j)].x;
+            const float rjj = (j & 1) ? a[j][diag_pair(j)].y : a[j][diag_pair(j)].x;
+            const float num = __shfl_sync(0xffffffffu, bj, gl + diag_lane(j)), den = __shfl_sync(0xffffffffu, rjj, gl + diag_lane(j));
             const float rden = rcp_nr(den);
             float xj = num * rden;
             xj = fmaf(fmaf(-xj, den, num), rden, xj);
             if (row0 < N) {            // only the lanes that hold rows of R
 #pragma unroll
-                for (int t = 0; t < NP; t++) {
-                    const int r0 = row0 + 2 * t, r1 = r0 + 1;
+                for (int t = 0; t < NPB; t++) {
+                    const int r0 = row_of(t), r1 = r0 + 1;
                     a[N][t].x = r0 == j ? xj : (r0 < j ? fmaf(-a[j][t].x, xj, a[N][t].x) : a[N][t].x);
                     a[N][t].y = r1 == j ? xj : (r1 < j ? fmaf(-a[j][t].y, xj, a[N][t].y) : a[N][t].y);
                 }
@@ -1291,14 +1367,14 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
             if (!GPUB_GELS_EARLY) {
 #pragma unroll
                 for (int c = 0; c < N; c++) {
-                    float4 *dc = reinterpret_cast<float4 *>(a_g + (size_t) c * M);
 #pragma unroll
-                    for (int vv = 0; vv < NV; vv++) dc[vv] = make_float4(a[c][2 * vv].x, a[c][2 * vv].y, a[c][2 * vv + 1].x, a[c][2 * vv + 1].y);
+                    for (int vv = 0; vv < NV; vv++)
+                        *reinterpret_cast<float4 *>(a_g + (size_t) c * M + vv * PS) = make_float4(a[c][2 * vv].x, a[c][2 * vv].y, a[c][2 * vv + 1].x, a[c][2 * vv + 1].y);
                 }
             }
-            float4 *dst = reinterpret_cast<float4 *>(b_g);
 #pragma unroll
-            for (int vv = 0; vv < NV; vv++) dst[vv] = make_float4(a[N][2 * vv].x, a[N][2 * vv].y, a[N][2 * vv + 1].x, a[N][2 * vv + 1].y);
+            for (int vv = 0; vv < NV; vv++)
+                *reinterpret_cast<float4 *>(b_g + vv * PS) = make_float4(a[N][2 * vv].x, a[N][2 * vv].y, a[N][2 * vv + 1].x, a[N][2 * vv + 1].y);
             if (info && l == 0) info[mat] = bad;
         }
     }
@@ -1311,9 +1387,16 @@ template<typename T, int M, int N, int LPM> struct GelsKernel {
 };
 template<int M, int N, int LPM> struct GelsKernel<float, M, N, LPM> {
     static void launch(unsigned grid, cudaStream_t stream, float *A, size_t sA, float *b, size_t sB, int *info, size_t batch) {
+        if (GPUB_GELS_TMA && sA == (size_t) M * N && sB == (size_t) M) {
+            // dense batch: bulk-copy staging, one resident wave that grid-strides (grid is a multiple of the SM count)
+            const size_t smem = (size_t) (128 / LPM) * (N + 1) * M * sizeof(float) + 64;
+            cudaFuncSetAttribute(k_gels_f2<M, N, LPM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            k_gels_f2<M, N, LPM, true><<<grid, 128, smem, stream>>>(A, sA, b, sB, info, batch);
+            return;
+        }
         const size_t smem = GPUB_GELS_STAGE ? (size_t) (128 / LPM) * (N + 1) * M * sizeof(float) : 0;   // one staged system per lane group
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gels_f2<M, N, LPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        k_gels_f2<M, N, LPM><<<grid, 128, smem, stream>>>(A, sA, b, sB, info, batch);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gels_f2<M, N, LPM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        k_gels_f2<M, N, LPM, false><<<grid, 128, smem, stream>>>(A, sA, b, sB, info, batch);
     }
 };
 
