@@ -258,7 +258,7 @@ public:
 
     void synchronizeStream(size_t idx = 0) const {
         if (idx >= m_numStreams) throw std::runtime_error("stream index out of range");
-        gpuErrChk(gpub_ctx_sync(m_ctx, static_cast<int>(idx)));
+        gpuErrChk(gpub_ctx_sync(contextOfCurrentDevice(), static_cast<int>(idx)));
     }
 
     void synchronizeAllStreams() const {

@@ -225,6 +225,75 @@ public:
     }
 };
 
+/**
+ * Additive API: Householder QR of every matrix of a (m, n, k)-tensor at once.
+ * The reference's QRFactoriser takes one matrix (it throws for k > 1, tensor.cuh:1811-1813) and its users loop over the
+ * batch with three library calls per matrix (BASELINE config 4: 256 x QRFactoriser). Here factorise() is ONE launch of the
+ * batched geqrf kernel and leastSquares() two (Q'b, then the triangular solves); storage and results per matrix are
+ * exactly those of QRFactoriser (LAPACK layout: R above, reflectors below the diagonal, tau per matrix).
+ */
+TEMPLATE_WITH_TYPE_T
+TEMPLATE_CONSTRAINT_REQUIRES_FPX
+class QRBatchFactoriser : public IStatus {
+private:
+    std::unique_ptr<DTensor<T> > m_householder; ///< tau (n, 1, k)
+    DTensor<T> *m_matrix;                       ///< matrices to factorise (not owned)
+
+public:
+    QRBatchFactoriser() = delete;
+
+    QRBatchFactoriser(DTensor<T> &A) : IStatus(A.numMats()) {
+        if (A.numRows() < A.numCols()) throw std::invalid_argument("[QRBatch] matrices must be tall or square");
+        m_matrix = &A;
+        m_householder = std::make_unique<DTensor<T> >(A.numCols(), 1, A.numMats(), true);
+    }
+
+    /** tau of every matrix, (n, 1, k). */
+    DTensor<T> &householder() { return *m_householder; }
+
+    void factorise() {
+        const size_t m = m_matrix->numRows(), n = m_matrix->numCols();
+        gpuErrChk(gpub200::Abi<T>::geqrf(gpub200::ctx(), (int) m_matrix->streamIdx(), m, n, m_matrix->raw(), m, m * n,
+                                         m_householder->raw(), n, m_matrix->numMats()));
+    }
+
+    /** C_i <- Q_i' C_i (transpose = true) or Q_i C_i; C is (m, c, k). */
+    void applyQ(DTensor<T> &C, bool transpose) {
+        const size_t m = m_matrix->numRows(), n = m_matrix->numCols(), k = m_matrix->numMats();
+        if (C.numRows() != m || C.numMats() != k) throw std::invalid_argument("[QRBatch] C incompatible with the factorised tensor");
+        gpuErrChk(gpub200::Abi<T>::ormqr(gpub200::ctx(), (int) m_matrix->streamIdx(), transpose ? 1 : 0, m, C.numCols(), n,
+                                         m_matrix->raw(), m, m * n, m_householder->raw(), n, C.raw(), m, m * C.numCols(), k));
+    }
+
+    /** rhs_i[0:n] <- argmin ||A_i x - rhs_i|| for every matrix; rhs is (m, 1, k) and is overwritten (Q_i' rhs_i, then solved). */
+    void leastSquares(DTensor<T> &rhs) {
+        const size_t m = m_matrix->numRows(), n = m_matrix->numCols(), k = m_matrix->numMats();
+        if (rhs.numRows() != m || rhs.numCols() != 1 || rhs.numMats() != k)
+            throw std::invalid_argument("[QRBatch] rhs must be (m, 1, k)");
+        applyQ(rhs, true);
+        gpuErrChk(gpub200::Abi<T>::trsv(gpub200::ctx(), (int) m_matrix->streamIdx(), n, m_matrix->raw(), m, m * n, rhs.raw(), m, k));
+    }
+
+    /** Debug helper, as QRFactoriser::getQR: explicit thin Q (m, n, k) and R (n, n, k). */
+    void getQR(DTensor<T> &Q, DTensor<T> &R) {
+        const size_t m = m_matrix->numRows(), n = m_matrix->numCols(), k = m_matrix->numMats();
+        if (Q.numRows() != m || Q.numCols() != n || Q.numMats() != k) throw std::invalid_argument("[QRBatch] invalid shape of Q.");
+        if (R.numRows() != n || R.numCols() != n || R.numMats() != k) throw std::invalid_argument("[QRBatch] invalid shape of R.");
+        std::vector<T> eye(m * n * k, T(0));
+        for (size_t i = 0; i < k; i++)
+            for (size_t c = 0; c < n; c++) eye[i * m * n + c + c * m] = T(1);
+        Q.upload(eye);
+        applyQ(Q, false);
+        std::vector<T> qr;
+        m_matrix->download(qr);
+        std::vector<T> upper(n * n * k, T(0));
+        for (size_t i = 0; i < k; i++)
+            for (size_t c = 0; c < n; c++)
+                for (size_t r = 0; r <= c; r++) upper[i * n * n + r + c * n] = qr[i * m * n + r + c * m];
+        R.upload(upper);
+    }
+};
+
 /* ================================================================================================
  *  Nullspace (N)
  * ================================================================================================ */
