@@ -113,7 +113,10 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 // N = 64, 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H. N = 64 is a whole warp per matrix with the
 // lower triangle in registers (96 entries per lane): no CTA barrier at all, which is what k_potrf_blk loses its time on.
 // DENSE: n == N and lda == N; otherwise rows / columns beyond n are an identity pad and lda is a run-time value.
-template<typename T, int N, bool DENSE = true> struct PotrfPairMinB { static constexpr int value = N == 64 ? (sizeof(T) == 8 ? 2 : (DENSE ? 4 : 3)) : GPUB_POTRF32_MINB; };
+#ifndef GPUB_PAIR64_F32_MINB
+#define GPUB_PAIR64_F32_MINB 4
+#endif
+template<typename T, int N, bool DENSE = true> struct PotrfPairMinB { static constexpr int value = N == 64 ? (sizeof(T) == 8 ? 2 : (DENSE ? GPUB_PAIR64_F32_MINB : 3)) : GPUB_POTRF32_MINB; };
 
 template<typename T, int N, bool DENSE>
 __global__ void __launch_bounds__(128, PotrfPairMinB<T, N, DENSE>::value) k_potrf_pair(int n_rt, T *A, size_t lda_rt, size_t strideA, int *info, size_t batch) {
@@ -204,7 +207,10 @@ __device__ unsigned long long g_chol_prof[8];
 #define CHOL_T(idx) do { } while (0)
 #endif
 // resident CTAs per SM the register allocation is tuned for
-template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : 2); };
+#ifndef GPUB_BLK4_F32_MINB
+#define GPUB_BLK4_F32_MINB 3
+#endif
+template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : (sizeof(T) == 4 ? GPUB_BLK4_F32_MINB : 2)); };
 
 template<typename T, int NB>
 __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_blk(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
@@ -958,7 +964,15 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
             k_potrf_flow<T, 2><<<grid, 32 * 3, smem, stream>>>((int) n, A, lda, strideA, info, batch);
         } else if (n <= 64) k_potrf_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, A, lda, strideA, info, batch);
         else if (n <= 96) k_potrf_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+#ifdef GPUB_POTRF_FLOW128
+        else {
+            const size_t smem = (size_t) 10 * 32 * 32 * sizeof(T);
+            GPUB_CUDA(cudaFuncSetAttribute(k_potrf_flow<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            k_potrf_flow<T, 4><<<grid, 32 * 10, smem, stream>>>((int) n, A, lda, strideA, info, batch);
+        }
+#else
         else k_potrf_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+#endif
     } else {
         const size_t bytes = n * n * sizeof(T);
         const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 1024 ? 1 : 0;
