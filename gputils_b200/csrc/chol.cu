@@ -212,13 +212,29 @@ __device__ unsigned long long g_chol_prof[8];
 #endif
 template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : (sizeof(T) == 4 ? GPUB_BLK4_F32_MINB : 2)); };
 
+// fp64: the trailing update runs on the FP64 tensor pipe (GPUB_BLK_DMMA). A block that still waits for its block column keeps
+// its 32 x 32 entries as 4 x 4 DMMA accumulator tiles (m8n8k4: lane (g, q) = (lane / 4, lane % 4) holds rows 8i + g, columns
+// 8j + 2q, 8j + 2q + 1); the rank-32 update is then 8 k-steps of (4 + 4) LDS.64 fragment loads and 16 DMMA instead of 32 k-steps
+// of 16 broadcast LDS.128 and 32 DFMA -- the lane = row form saturated the shared-memory writeback path (ncu / phase timers:
+// trailing 34 % of a matrix). When the block's own column comes up it is turned into the lane = row form once, through its
+// (free) panel slot. The panel slots have a row stride of 36 doubles so that the fragment loads are bank-conflict free.
+#ifndef GPUB_BLK_DMMA
+#define GPUB_BLK_DMMA 1
+#endif
+__device__ __forceinline__ void chol_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 template<typename T, int NB>
 __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_blk(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
     constexpr int NW = NB * (NB + 1) / 2;
-    __shared__ __align__(16) T s_p[NB][32][32]; // panel blocks of the current block column: [block row][k][row]
+    constexpr bool FRAG = GPUB_BLK_DMMA && sizeof(T) == 8;   // trailing blocks in DMMA accumulator layout
+    constexpr int LDP = FRAG ? 36 : 32;                      // row stride of a panel slot
+    __shared__ __align__(16) T s_p[NB][32][LDP]; // panel blocks of the current block column: [block row][k][row]
     __shared__ T s_rinv[32];
     __shared__ int s_bad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
     // enumerate the lower-triangular blocks: warp -> (rb, h), rb >= h
     int rb = 0;
     while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
@@ -231,16 +247,44 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         T *a_g = A + mat * strideA;
         T a[32];
+        if (FRAG && h > 0) {
+            // accumulator layout: a[(4 i + j) * 2 + e] = entry (8 i + g, 8 j + 2 q + e) of the block
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-            const int col = 32 * h + c;
-            a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int r_ = 32 * rb + 8 * i + g, c_ = 32 * h + 8 * j + 2 * q + e;
+                        a[(4 * i + j) * 2 + e] = (r_ < n && c_ <= r_) ? a_g[r_ + (size_t) c_ * lda] : T(r_ == c_ ? 1 : 0);
+                    }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int col = 32 * h + c;
+                a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
+            }
         }
         if (threadIdx.x == 0) s_bad = 0;
         __syncthreads();
         CHOL_T(0);
 #pragma unroll 1
         for (int hb = 0; hb < NB; hb++) {
+            if (FRAG && h == hb && hb > 0) {
+                // this block's column has come up: accumulator tiles -> lane = row, through the block row's panel slot (free since
+                // the barrier that closed block column hb - 1)
+                T *scr = &s_p[rb][0][0];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) scr[(8 * j + 2 * q + e) * LDP + 8 * i + g] = a[(4 * i + j) * 2 + e];
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 32; c++) a[c] = scr[c * LDP + lane];
+                __syncwarp();
+            }
             if (rb == hb && h == hb) { // (1) diagonal block
                 int bad = 0;
                 T d = __shfl_sync(0xffffffffu, a[0], 0);   // pivot chain kept out of shared memory, see k_potrf_group
@@ -274,11 +318,31 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
             __syncthreads();
             CHOL_T(2);
             if (h > hb) { // (3) trailing blocks (rb >= h > hb)
-#pragma unroll 8
-                for (int k = 0; k < 32; k++) {
-                    const T lk = s_p[rb][k][lane];
+                if constexpr (FRAG) {
+#pragma unroll 2
+                    for (int k4 = 0; k4 < 32; k4 += 4) {
+                        double af[4], bf[4];
 #pragma unroll
-                    for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[h][k][c], a[c]);
+                        for (int i = 0; i < 4; i++) af[i] = -(double) s_p[rb][k4 + q][8 * i + g];   // A(row g, k q) = L(rb, hb)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) bf[j] = (double) s_p[h][k4 + q][8 * j + g];     // B(k q, col g) = L(h, hb)^T
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                double c0 = (double) a[(4 * i + j) * 2], c1 = (double) a[(4 * i + j) * 2 + 1];
+                                chol_dmma(c0, c1, af[i], bf[j]);
+                                a[(4 * i + j) * 2] = (T) c0;
+                                a[(4 * i + j) * 2 + 1] = (T) c1;
+                            }
+                    }
+                } else {
+#pragma unroll 8
+                    for (int k = 0; k < 32; k++) {
+                        const T lk = s_p[rb][k][lane];
+#pragma unroll
+                        for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[h][k][c], a[c]);
+                    }
                 }
             }
             __syncthreads();
