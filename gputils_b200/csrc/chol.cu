@@ -39,6 +39,27 @@ template<> __device__ __forceinline__ float fast_rsqrt<float>(float d) {
     return fmaf(0.5f * r, fmaf(-d * r, r, 1.0f), r); // one Newton step: rsqrtf alone is ~2 ulp
 }
 
+template<typename T> __device__ __forceinline__ T fast_rcp(T d);
+template<> __device__ __forceinline__ double fast_rcp<double>(double d) {
+    // MUFU.RCP64H seed + two Newton steps y <- y + y (1 - d y)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    y = fma(y, fma(-d, y, 1.0), y);
+    y = fma(y, fma(-d, y, 1.0), y);
+    return y;
+}
+template<> __device__ __forceinline__ float fast_rcp<float>(float d) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    return fmaf(y, fmaf(-d, y, 1.0f), y);
+}
+// GPUB_DIAG_TILED = 1: 4-column steps with the 4 x 4 diagonal tile factorised redundantly in every lane (see factor_diag in
+// k_potrf_blk). Measured slower (n = 128: fp64 0.86 -> 1.06 ms, fp32 1.17 -> 1.36 ms): the chain per column is shorter, but the
+// diagonal warp runs alone and its time is set by its instruction count (2180 instead of 1440 per 32 x 32 block, ~5 cycles each).
+#ifndef GPUB_DIAG_TILED
+#define GPUB_DIAG_TILED 0
+#endif
+
 // ------------------------------------------------------------------------------------------
 // potrf, n <= 32: NP lanes per matrix
 // Control flow is uniform across the CTA (tail groups redo the last matrix with stores masked) and the
@@ -231,6 +252,7 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
     constexpr bool FRAG = GPUB_BLK_DMMA && sizeof(T) == 8;   // trailing blocks in DMMA accumulator layout
     constexpr int LDP = FRAG ? 36 : 32;                      // row stride of a panel slot
     __shared__ __align__(16) T s_p[NB][32][LDP]; // panel blocks of the current block column: [block row][k][row]
+    __shared__ __align__(16) T s_d[32][LDP];     // factor of the current diagonal block, [k][row]
     __shared__ T s_rinv[32];
     __shared__ int s_bad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -247,6 +269,93 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         T *a_g = A + mat * strideA;
         T a[32];
+        // accumulator tiles -> lane = row, through a scratch slot nobody reads at that time
+        auto to_rows = [&](T *scr) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) scr[(8 * j + 2 * q + e) * LDP + 8 * i + g] = a[(4 * i + j) * 2 + e];
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 32; c++) a[c] = scr[c * LDP + lane];
+            __syncwarp();
+        };
+        // The diagonal warp of block column hb: 32 x 32 factorisation in 4-column steps, factor and reciprocal pivots left in shared
+        // memory. The serial chain of a column-by-column factorisation is pivot shuffle -> rsqrt -> scale -> broadcast (~240 cycles
+        // per column with nine warps waiting). Here the 4 x 4 diagonal tile of a step is gathered into EVERY lane (10 shuffles in
+        // flight together) and factorised redundantly in registers: the pivots follow the LDL^T recurrence d_k = D_kk - sum u_kj^2 / d_j
+        // through reciprocals, so the four rsqrt (for the L entries) hang off the chain instead of sitting in it; each lane then
+        // solves its own row against the tile and one shared-memory round publishes the 4 columns for the rank-4 update.
+        auto factor_diag = [&](int hb) {
+            int bad = 0;
+#if GPUB_DIAG_TILED
+            auto tile_step = [&](auto c0_tag) {
+                constexpr int c0 = decltype(c0_tag)::value;
+                T D[4][4];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int r = c; r < 4; r++) D[r][c] = __shfl_sync(0xffffffffu, a[c0 + c], c0 + r);
+                // unnormalised columns u (in place in D), pivots d_k on the diagonal, reciprocals iv, rsqrt rs
+                T iv[4], rs[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (!(D[k][k] > T(0)) && bad == 0) bad = c0 + k + 1;
+                    iv[k] = fast_rcp<T>(D[k][k]);
+                    rs[k] = fast_rsqrt<T>(D[k][k]);
+#pragma unroll
+                    for (int c = k + 1; c < 4; c++) {
+                        const T m = D[c][k] * iv[k];
+#pragma unroll
+                        for (int r = c; r < 4; r++) D[r][c] = fma(-D[r][k], m, D[r][c]);
+                    }
+                }
+                // this lane's row against the tile: x_c = (a_c - sum_{k<c} x_k l_ck) / l_cc with l_ck = u_ck rs_k
+                T x[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    T acc = a[c0 + c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) acc = fma(-x[k], D[c][k] * rs[k], acc);
+                    x[c] = acc * rs[c];
+                    a[c0 + c] = x[c];
+                    s_d[c0 + c][lane] = x[c];
+                }
+                if (lane < 4) s_rinv[c0 + lane] = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
+                __syncwarp();
+#pragma unroll
+                for (int c = c0 + 4; c < 32; c++) {
+                    T acc = a[c];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) acc = fma(-x[k], s_d[c0 + k][c], acc);
+                    a[c] = acc;
+                }
+            };
+            // explicit unrolling: every index into a[] must be a compile-time constant to stay in registers
+            tile_step(std::integral_constant<int, 0>{}); tile_step(std::integral_constant<int, 4>{});
+            tile_step(std::integral_constant<int, 8>{}); tile_step(std::integral_constant<int, 12>{});
+            tile_step(std::integral_constant<int, 16>{}); tile_step(std::integral_constant<int, 20>{});
+            tile_step(std::integral_constant<int, 24>{}); tile_step(std::integral_constant<int, 28>{});
+#else
+            T d = __shfl_sync(0xffffffffu, a[0], 0);   // pivot chain kept out of shared memory, see k_potrf_group
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                if (!(d > T(0)) && bad == 0) bad = j + 1;
+                const T r = fast_rsqrt<T>(d);
+                const T l = a[j] * r;
+                a[j] = l;
+                if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
+                s_d[j][lane] = l;
+                if (lane == j) s_rinv[j] = r;
+                __syncwarp();
+#pragma unroll
+                for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+            }
+#endif
+            if (lane == 0 && bad != 0) atomicCAS(&s_bad, 0, 32 * hb + bad);   // block columns finish in order: the first one to fail wins
+        };
         if (FRAG && h > 0) {
             // accumulator layout: a[(4 i + j) * 2 + e] = entry (8 i + g, 8 j + 2 q + e) of the block
 #pragma unroll
@@ -268,51 +377,22 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
         if (threadIdx.x == 0) s_bad = 0;
         __syncthreads();
         CHOL_T(0);
+        if (warp == 0) factor_diag(0);
+        __syncthreads();
+        CHOL_T(1);
+        // Per block column two barriers: (2) panel solves, then (3) trailing updates -- and the warp of the NEXT diagonal block
+        // factorises it as soon as its own update is done, while the other trailing warps are still updating (look-ahead).
 #pragma unroll 1
-        for (int hb = 0; hb < NB; hb++) {
-            if (FRAG && h == hb && hb > 0) {
-                // this block's column has come up: accumulator tiles -> lane = row, through the block row's panel slot (free since
-                // the barrier that closed block column hb - 1)
-                T *scr = &s_p[rb][0][0];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) scr[(8 * j + 2 * q + e) * LDP + 8 * i + g] = a[(4 * i + j) * 2 + e];
-                __syncwarp();
-#pragma unroll
-                for (int c = 0; c < 32; c++) a[c] = scr[c * LDP + lane];
-                __syncwarp();
-            }
-            if (rb == hb && h == hb) { // (1) diagonal block
-                int bad = 0;
-                T d = __shfl_sync(0xffffffffu, a[0], 0);   // pivot chain kept out of shared memory, see k_potrf_group
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if (!(d > T(0)) && bad == 0) bad = j + 1;
-                    const T r = fast_rsqrt<T>(d);
-                    const T l = a[j] * r;
-                    a[j] = l;
-                    if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
-                    s_p[hb][j][lane] = l;
-                    if (lane == j) s_rinv[j] = r;
-                    __syncwarp();
-#pragma unroll
-                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[hb][j][c], a[c]);
-                }
-                if (lane == 0 && bad != 0 && s_bad == 0) s_bad = 32 * hb + bad;
-            }
-            __syncthreads();
-            CHOL_T(1);
+        for (int hb = 0; hb + 1 < NB; hb++) {
             if (h == hb && rb > hb) { // (2) panel blocks: rows below the diagonal block
+                if (FRAG && hb > 0) to_rows(&s_p[rb][0][0]);   // the block row's slot is free since the barrier that closed column hb - 1
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const T l = a[j] * s_rinv[j];
                     a[j] = l;
                     s_p[rb][j][lane] = l;
 #pragma unroll
-                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[hb][j][c], a[c]);
+                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
                 }
             }
             __syncthreads();
@@ -343,6 +423,10 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 #pragma unroll
                         for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[h][k][c], a[c]);
                     }
+                }
+                if (rb == hb + 1 && h == hb + 1) {   // the next diagonal block is complete: factorise it now
+                    if (FRAG) to_rows(&s_d[0][0]);   // s_d was last read by the panel solves of column hb, which are behind a barrier
+                    factor_diag(hb + 1);
                 }
             }
             __syncthreads();
