@@ -242,6 +242,9 @@ template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = 
 #ifndef GPUB_BLK_DMMA
 #define GPUB_BLK_DMMA 1
 #endif
+#ifndef GPUB_POTRF_PIPE
+#define GPUB_POTRF_PIPE 1
+#endif
 __device__ __forceinline__ void chol_dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -442,6 +445,180 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
         if (threadIdx.x == 0) info[mat] = s_bad;
         __syncthreads();
         CHOL_T(4);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// potrf, 64 < n <= 32*NB, PIPELINED version: k_potrf_pipe<T, NB>. Same block ownership, arithmetic and DMMA trailing update as
+// k_potrf_blk, but ONE CTA barrier per block column. In the interval of block column hb
+//   * every warp with h >= hb first applies the rank-32 update of block column hb - 1 to its block,
+//   * the diagonal warp (hb, hb) then factorises its block column by column and publishes its progress (a counter in shared
+//     memory, written after the column and its reciprocal pivot are in place),
+//   * the panel warps (rb > hb, hb) follow it one column behind: column j of the panel solve needs only column j of L11, so the
+//     panel solves finish ~100 cycles after the diagonal block instead of a whole phase later.
+// k_potrf_blk's stall samples were 72 % barrier waits, most of them nine warps waiting for the diagonal warp; here the panel
+// phase (18 % of a matrix) disappears from the critical path: per block column it is update + diagonal block.
+// The panel slots are double-buffered by block-column parity (the trailing warps of column hb - 1 still read L(., hb - 1) while
+// the panel warps of column hb write L(., hb)); the only spinning is the panel warps' poll of the progress counter, inside one
+// CTA, on a warp that never waits for them.
+// ------------------------------------------------------------------------------------------
+// The progress signal is an mbarrier per chunk of GPUB_PIPE_CHUNK columns (count 1): the diagonal warp's lane 0 arrives (release)
+// after the __syncwarp that follows the chunk's last column store, a panel warp sleeps in try_wait (acquire) -- no polling loop
+// competing for issue slots and, unlike a flag + __threadfence_block (MEMBAR.CTA in front of the next LDS of the chain, measured
+// 0.86 -> 1.09 ms), nothing on the diagonal warp's dependency chain.
+#ifndef GPUB_PIPE_CHUNK
+#define GPUB_PIPE_CHUNK 4
+#endif
+__device__ __forceinline__ void chol_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void chol_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void chol_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "CHOL_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CHOL_DONE_%=;\n\t"
+        "bra CHOL_WAIT_%=;\n\t"
+        "CHOL_DONE_%=:\n\t}" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template<typename T, int NB>
+__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_pipe(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
+    constexpr bool FRAG = GPUB_BLK_DMMA && sizeof(T) == 8;   // trailing blocks in DMMA accumulator layout
+    constexpr int LDP = FRAG ? 36 : 32;                      // row stride of a panel slot
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T (*s_p)[NB][32][LDP] = reinterpret_cast<T (*)[NB][32][LDP]>(smem_raw);                              // [parity][block row][k][row]
+    T (*s_d)[LDP] = reinterpret_cast<T (*)[LDP]>(smem_raw + sizeof(T) * 2 * NB * 32 * LDP);              // current diagonal factor [k][row]
+    T *s_rinv = reinterpret_cast<T *>(smem_raw + sizeof(T) * (2 * NB + 1) * 32 * LDP);
+    __shared__ int s_bad;
+    __shared__ __align__(8) uint64_t s_bar[32 / GPUB_PIPE_CHUNK];   // chunk c of the current diagonal block is published
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    int rb = 0;
+    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
+    const int h = warp - rb * (rb + 1) / 2;
+    const int row = 32 * rb + lane;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 32 / GPUB_PIPE_CHUNK; c++) chol_mbar_init(&s_bar[c], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned use = 0;        // diagonal blocks factorised so far by this CTA: every barrier completes one phase per block
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *a_g = A + mat * strideA;
+        T a[32];
+        if (FRAG && h > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int r_ = 32 * rb + 8 * i + g, c_ = 32 * h + 8 * j + 2 * q + e;
+                        a[(4 * i + j) * 2 + e] = (r_ < n && c_ <= r_) ? a_g[r_ + (size_t) c_ * lda] : T(r_ == c_ ? 1 : 0);
+                    }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int col = 32 * h + c;
+                a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
+            }
+        }
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int hb = 0; hb < NB; hb++, use++) {
+            if (h >= hb) {
+                if (hb > 0) { // rank-32 update with block column hb - 1
+                    const int pp = (hb - 1) & 1;
+                    if constexpr (FRAG) {
+#pragma unroll 2
+                        for (int k4 = 0; k4 < 32; k4 += 4) {
+                            double af[4], bf[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) af[i] = -(double) s_p[pp][rb][k4 + q][8 * i + g];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) bf[j] = (double) s_p[pp][h][k4 + q][8 * j + g];
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    double c0 = (double) a[(4 * i + j) * 2], c1 = (double) a[(4 * i + j) * 2 + 1];
+                                    chol_dmma(c0, c1, af[i], bf[j]);
+                                    a[(4 * i + j) * 2] = (T) c0;
+                                    a[(4 * i + j) * 2 + 1] = (T) c1;
+                                }
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int k = 0; k < 32; k++) {
+                            const T lk = s_p[pp][rb][k][lane];
+#pragma unroll
+                            for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[pp][h][k][c], a[c]);
+                        }
+                    }
+                }
+                if (h == hb) {
+                    if (FRAG && hb > 0) {
+                        // accumulator tiles -> lane = row through a slot nobody reads now: the diagonal warp uses s_d (its readers wait on
+                        // the chunk barriers first), a panel warp its own slot of this column's parity
+                        T *scr = rb == hb ? &s_d[0][0] : &s_p[hb & 1][rb][0][0];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) scr[(8 * j + 2 * q + e) * LDP + 8 * i + g] = a[(4 * i + j) * 2 + e];
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 32; c++) a[c] = scr[c * LDP + lane];
+                        __syncwarp();
+                    }
+                    if (rb == hb) { // diagonal block
+                        int bad = 0;
+                        T d = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if (!(d > T(0)) && bad == 0) bad = j + 1;
+                            const T r = fast_rsqrt<T>(d);
+                            const T l = a[j] * r;
+                            a[j] = l;
+                            if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
+                            s_d[j][lane] = l;
+                            if (lane == j) s_rinv[j] = r;
+                            __syncwarp();
+                            if ((j + 1) % GPUB_PIPE_CHUNK == 0 && lane == 0) chol_mbar_arrive(&s_bar[j / GPUB_PIPE_CHUNK]);
+#pragma unroll
+                            for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+                        }
+                        if (lane == 0 && bad != 0) atomicCAS(&s_bad, 0, 32 * hb + bad);
+                    } else { // panel block: one column behind the diagonal warp
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if (j % GPUB_PIPE_CHUNK == 0) chol_mbar_wait(&s_bar[j / GPUB_PIPE_CHUNK], use & 1u);
+                            const T l = a[j] * s_rinv[j];
+                            a[j] = l;
+                            s_p[hb & 1][rb][j][lane] = l;
+#pragma unroll
+                            for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (row < n) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int col = 32 * h + c;
+                if (col <= row) a_g[row + (size_t) col * lda] = a[c];
+            }
+        }
+        if (threadIdx.x == 0) info[mat] = s_bad;
+        __syncthreads();
     }
 }
 
@@ -1111,7 +1288,16 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
             const size_t smem = (size_t) 3 * 32 * 32 * sizeof(T);
             k_potrf_flow<T, 2><<<grid, 32 * 3, smem, stream>>>((int) n, A, lda, strideA, info, batch);
         } else if (n <= 64) k_potrf_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, A, lda, strideA, info, batch);
-        else if (n <= 96) k_potrf_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+        else if (n <= 96) {
+#if GPUB_POTRF_PIPE
+            constexpr int LDPH = (GPUB_BLK_DMMA && sizeof(T) == 8) ? 36 : 32;
+            const size_t smem = sizeof(T) * ((size_t) (2 * 3 + 1) * 32 * LDPH + 32);
+            GPUB_CUDA(cudaFuncSetAttribute(k_potrf_pipe<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            k_potrf_pipe<T, 3><<<grid, 32 * 6, smem, stream>>>((int) n, A, lda, strideA, info, batch);
+#else
+            k_potrf_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+#endif
+        }
 #ifdef GPUB_POTRF_FLOW128
         else {
             const size_t smem = (size_t) 10 * 32 * 32 * sizeof(T);
@@ -1119,7 +1305,16 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
             k_potrf_flow<T, 4><<<grid, 32 * 10, smem, stream>>>((int) n, A, lda, strideA, info, batch);
         }
 #else
-        else k_potrf_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+        else {
+#if GPUB_POTRF_PIPE
+            constexpr int LDPH = (GPUB_BLK_DMMA && sizeof(T) == 8) ? 36 : 32;
+            const size_t smem = sizeof(T) * ((size_t) (2 * 4 + 1) * 32 * LDPH + 32);
+            GPUB_CUDA(cudaFuncSetAttribute(k_potrf_pipe<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            k_potrf_pipe<T, 4><<<grid, 32 * 10, smem, stream>>>((int) n, A, lda, strideA, info, batch);
+#else
+            k_potrf_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, A, lda, strideA, info, batch);
+#endif
+        }
 #endif
     } else {
         const size_t bytes = n * n * sizeof(T);

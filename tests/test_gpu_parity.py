@@ -70,7 +70,9 @@ def test_gemm_output_aliasing_rhs(gpu_ctx, dt, n, batch):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("n,batch", [(1, 5), (2, 9), (3, 2), (4, 1000), (5, 77), (8, 1000), (13, 50), (16, 513), (20, 33),
-                                     (32, 1000), (32, 1), (33, 7), (64, 10), (100, 3), (128, 4), (200, 2)])
+                                     (32, 1000), (32, 1), (33, 7), (64, 10), (100, 3), (128, 4), (200, 2),
+                                     # more matrices than resident CTAs: every CTA of the persistent kernels walks several matrices
+                                     (128, 2600), (96, 2500), (70, 2400), (48, 5000)])
 def test_potrf_potrs(gpu_ctx, oracle, dt, n, batch):
     import torch
     from gputils_b200 import capi
@@ -93,7 +95,7 @@ def test_potrf_potrs(gpu_ctx, oracle, dt, n, batch):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("n", [3, 8, 32, 40])
+@pytest.mark.parametrize("n", [3, 8, 32, 40, 96, 128])
 def test_potrf_reports_first_bad_pivot(gpu_ctx, oracle, dt, n):
     import torch
     from gputils_b200 import capi
