@@ -36,7 +36,7 @@ REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
 N_MAT = 32
-# DRAM bytes per 32 x 32 fp64 matrix of k_potrf_group, measured with ncu (profiles/r1e_ncu_chol32.json):
+# DRAM bytes per 32 x 32 fp64 matrix of k_potrf_group, measured with ncu (profiles/r1h_ncu_chol32.json):
 # (1.550705 + 1.151753) GB over 250,000 matrices (k_potrf_pair<double,32>)
 POTRF_DRAM_BYTES_PER_MATRIX = 10809.8
 SEED_A, SEED_B = 0x5EED0002, 0x5EED0102
@@ -402,7 +402,7 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (POTRF_DRAM_BYTES_PER_MATRIX * k if args.impl == "ours" else None),
                          "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the potrf kernel: "
-                                            "profiles/r1e_ncu_chol32.json (only the lower triangle moves)" if args.impl == "ours" else None),
+                                            "profiles/r1h_ncu_chol32.json (only the lower triangle moves)" if args.impl == "ours" else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": potrf_bytes,
                          "frac_of_8TBs_nominal": achieved / 8000.0},
             "clocks": clocks,

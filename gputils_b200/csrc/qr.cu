@@ -13,6 +13,9 @@
 //   k_geqrf_cta / k_gels_cta / k_ormqr_cta / k_trsv_cta : any shape, one matrix per CTA, staged in shared
 //        memory when it fits, else in place in global memory (L2 resident).
 #include "common.cuh"
+#ifndef GPUB_GRID_WAVES
+#define GPUB_GRID_WAVES 2   // persistent grids: resident CTAs per SM x SM count x this
+#endif
 
 namespace {
 
@@ -1501,7 +1504,7 @@ int trsv_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *R, size_t ldr, siz
 template<typename T, int M, int N, int LPM>
 int launch_gels_sub(gpub_ctx_t ctx, cudaStream_t stream, T *A, size_t sA, T *b, size_t sB, int *info, size_t batch) {
     const size_t want = gpub_ceil_div(batch, (size_t) (128 / LPM));
-    const size_t cap = (size_t) ctx->sm_count * GPUB_GELS_MINB * 2;
+    const size_t cap = (size_t) ctx->sm_count * GPUB_GELS_MINB * GPUB_GRID_WAVES;
     const unsigned grid = (unsigned) (want < cap ? want : cap);
     GelsKernel<T, M, N, LPM>::launch(grid, stream, A, sA, b, sB, info, batch);
     GPUB_LAUNCH_CHECK();

@@ -12,7 +12,7 @@ ncu --set full --clock-control none -k regex:"k_geqrf_tc" -c 1 -o gpurun_out/${t
 ncu --set full --clock-control none -k regex:"k_gels_f2" -c 1 -o gpurun_out/${tag}_prof_gels python scripts/bench_ops.py --ops gels --reps 1 --scale 0.25 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_jacobi_rt|k_ormqr_tc|k_gemv|k_gemm_dmma" -c 6 -o gpurun_out/${tag}_prof_svd python scripts/bench_ops.py --ops svdu,nullspace --reps 1 --scale 0.125 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_gemm_col" -s 5 -c 1 -o gpurun_out/${tag}_prof_gemm8 python scripts/bench_ops.py --ops gemm --reps 1 > /dev/null 2>&1
-ncu --set full --clock-control none -k regex:"k_potrf_pair|k_potrs_pair64|k_potrf_blk|k_potrs_quad128" -c 8 -o gpurun_out/${tag}_prof_chol64 python scripts/bench_ops.py --ops cholsweep --reps 1 --scale 0.125 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:"k_potrf_pair|k_potrs_pair64|k_potrf_pipe|k_potrs_quad128" -c 8 -o gpurun_out/${tag}_prof_chol64 python scripts/bench_ops.py --ops cholsweep --reps 1 --scale 0.125 > /dev/null 2>&1
 # keep what travels back small (gpurun merges at most 64 MiB): summarise every capture here and drop the .ncu-rep
 for f in gpurun_out/${tag}_prof_*.ncu-rep; do
     python scripts/ncu_raw.py $f --json ${f%.ncu-rep}.json > /dev/null 2>&1
