@@ -564,6 +564,12 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), MINB) k_sgemm_rt(size_t
     }
 }
 
+#ifndef GPUB_SGEMM64_TN
+#define GPUB_SGEMM64_TN 8
+#endif
+#ifndef GPUB_SGEMM64_MINB
+#define GPUB_SGEMM64_MINB 6
+#endif
 template<typename T>
 bool try_sgemm_rt(gpub_ctx_t, cudaStream_t, size_t, size_t, size_t, T, const T *, size_t, size_t, const T *, size_t, size_t, T, T *,
                   size_t, size_t, size_t) { return false; }
@@ -575,6 +581,8 @@ bool try_sgemm_rt<float>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n
                     sA % 4 == 0 && sB % 4 == 0 && sC % 4 == 0;
     if (!al || k % 16 != 0 || k < 16) return false;
     const size_t cap = (size_t) ctx->sm_count * 8;
+    const size_t cap2 = (size_t) ctx->sm_count * GPUB_SGEMM64_MINB * 2;
+    (void) cap2;
     if (m % 128 == 0 && n % 128 == 0) {
         const size_t tm = m / 128, tn = n / 128, total = tm * tn * batch;
         k_sgemm_rt<128, 128, 8, 8, 2><<<(unsigned) (total < cap ? total : cap), 256, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
@@ -582,7 +590,12 @@ bool try_sgemm_rt<float>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t n
     }
     if (m % 64 == 0 && n % 64 == 0) {
         const size_t tm = m / 64, tn = n / 64, total = tm * tn * batch;
+#if GPUB_SGEMM64_TN == 8
+        // 8 x 8 thread tiles on 64 threads: the 8 x 4 tile needs 12 LDS.128 per 64 FFMA2 and is bound by shared-memory wavefronts
+        k_sgemm_rt<64, 64, 8, 8, GPUB_SGEMM64_MINB><<<(unsigned) (total < cap2 ? total : cap2), 64, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+#else
         k_sgemm_rt<64, 64, 8, 4, 1><<<(unsigned) (total < cap ? total : cap), 128, 0, stream>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, tm, tn, batch);
+#endif
         return true;
     }
     return false;

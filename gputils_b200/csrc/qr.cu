@@ -940,7 +940,14 @@ bool try_geqrf_tc<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t m, size_t 
     const size_t ldv = (m + 15) / 16 * 16 + 8;   // = 8 (mod 16): the 128-bit fragment loads of pass 1 are bank-conflict free
     const size_t smem = ((size_t) TCQ_OFF_VS + TCQ_NB * ldv) * sizeof(double);
     if (smem > (size_t) ctx->max_smem_optin) return false;
-    const unsigned grid = (unsigned) (batch < (size_t) ctx->sm_count ? batch : (size_t) ctx->sm_count);
+    // one CTA per SM, every CTA the same number of matrices: 256 matrices run as 2 x 128 rather than 148 + 108 -- the makespan in
+    // matrices is the same, but the matrices in flight (1 MB each) then fit the 126 MB L2, which the trailing passes re-read
+    const size_t waves = gpub_ceil_div(batch, (size_t) ctx->sm_count);
+#ifdef GPUB_TCQ_GRID
+    const unsigned grid = (unsigned) (batch < (size_t) GPUB_TCQ_GRID ? batch : (size_t) GPUB_TCQ_GRID);
+#else
+    const unsigned grid = (unsigned) gpub_ceil_div(batch, waves);
+#endif
     cudaError_t e;
     if (m <= 512) {
         e = cudaFuncSetAttribute(k_geqrf_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
