@@ -137,6 +137,9 @@ k_potrf_group(int n, T *A, size_t lda_rt, size_t strideA, int *info, size_t batc
 // N = 64, 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H. N = 64 is a whole warp per matrix with the
 // lower triangle in registers (96 entries per lane): no CTA barrier at all, which is what k_potrf_blk loses its time on.
 // DENSE: n == N and lda == N; otherwise rows / columns beyond n are an identity pad and lda is a run-time value.
+#ifndef GPUB_QUAD128_F32_MINB
+#define GPUB_QUAD128_F32_MINB 4
+#endif
 #ifndef GPUB_PAIR64_F32_MINB
 #define GPUB_PAIR64_F32_MINB 4
 #endif
@@ -1122,7 +1125,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(in
 // Five CTA barriers per matrix instead of the sixteen of k_potrs_blk<T, 4>, and no warp ever waits inside a 32-column block.
 // ------------------------------------------------------------------------------------------
 template<typename T>
-__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 3) k_potrs_quad128(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b,
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MINB) k_potrs_quad128(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b,
                                                                                 size_t strideB, size_t batch) {
     __shared__ T s_t[2][32][33];
     __shared__ __align__(16) T s_x[128];       // scaled right-hand side -> y -> v
