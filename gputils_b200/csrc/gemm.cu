@@ -362,8 +362,9 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // TRB: the second operand is given transposed (B = Bt^T with Bt n x k column-major, ldb its leading dimension): the
 // panel then lands as [kk][col] like A's and its fragments are read with A's conflict-free pattern (P = N N^T).
 // DKT: depth of a K panel (16 or 32; 32 halves the number of CTA barriers per tile and needs dynamic shared memory)
-template<bool TRB, int DKT>
-__global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
+// WARPS: 8 warps of 16 x 32 warp tiles (6 fragment loads per 8 DMMA) or 4 warps of 32 x 32 (8 per 16)
+template<bool TRB, int DKT, int WARPS = 8>
+__global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
                                                     size_t tiles_n, size_t batch) {
@@ -373,7 +374,8 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
     double (*As)[DKT][DLD] = reinterpret_cast<double (*)[DKT][DLD]>(smem_raw);
     double (*Bs)[BROWS][BLD] = reinterpret_cast<double (*)[BROWS][BLD]>(smem_raw + sizeof(double) * 2 * DKT * DLD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = (warp & 3) * 16, wc = (warp >> 2) * 32; // warp origin inside the tile
+    constexpr int NTH = 32 * WARPS, WM = WARPS == 8 ? 16 : 32, MI = WM / 8, WR = 64 / WM;
+    const int wr = (warp % WR) * WM, wc = (warp / WR) * 32; // warp origin inside the tile
     const int g = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
     const size_t tiles = tiles_m * tiles_n;
     for (size_t t = blockIdx.x; t < tiles * batch; t += gridDim.x) {
@@ -381,24 +383,24 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
         const size_t row0 = (r % tiles_m) * 64, col0 = (r / tiles_m) * 64;
         const double *a = A + b * sA + row0;
         const double *bb = B + b * sB + (TRB ? col0 : col0 * ldb);
-        double acc[2][4][2];
+        double acc[MI][4][2];
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < MI; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         auto load_panel = [&](int buf, size_t k0) {
             // A: DKT columns of 64 rows = 32 DKT double2 ; 256 threads x DKT / 8
 #pragma unroll
-            for (int l = 0; l < DKT / 8; l++) {
-                int e = threadIdx.x + l * 256;
+            for (int l = 0; l < 32 * DKT / NTH; l++) {
+                int e = threadIdx.x + l * NTH;
                 int rr = (e & 31) * 2, kk = e >> 5;
                 cp_async16(&As[buf][kk][rr], a + rr + (k0 + kk) * lda);
             }
             // B: 64 columns of DKT k = 32 DKT double2
 #pragma unroll
-            for (int l = 0; l < DKT / 8; l++) {
-                int e = threadIdx.x + l * 256;
+            for (int l = 0; l < 32 * DKT / NTH; l++) {
+                int e = threadIdx.x + l * NTH;
                 if (TRB) {
                     int cc = (e & 31) * 2, kk = e >> 5;
                     cp_async16(&Bs[buf][kk][cc], bb + cc + (k0 + kk) * ldb);
@@ -423,13 +425,13 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
             __syncthreads();
 #pragma unroll
             for (int k4 = 0; k4 < DKT; k4 += 4) {
-                double af[2], bf[4];
+                double af[MI], bf[4];
 #pragma unroll
-                for (int i = 0; i < 2; i++) af[i] = As[buf][k4 + q][wr + 8 * i + g]; // A(row g, k q)
+                for (int i = 0; i < MI; i++) af[i] = As[buf][k4 + q][wr + 8 * i + g]; // A(row g, k q)
 #pragma unroll
                 for (int j = 0; j < 4; j++) bf[j] = TRB ? Bs[buf][k4 + q][wc + 8 * j + g] : Bs[buf][wc + 8 * j + g][k4 + q]; // B(k q, col g)
 #pragma unroll
-                for (int i = 0; i < 2; i++)
+                for (int i = 0; i < MI; i++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(256) k_gemm_dmma(size_t m, size_t n, size_t k,
         }
         double *c = C + b * sC;
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < MI; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 size_t gr = row0 + wr + 8 * i + g;
@@ -564,6 +566,12 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), MINB) k_sgemm_rt(size_t
     }
 }
 
+#ifndef GPUB_DMMA_WARPS
+#define GPUB_DMMA_WARPS 4
+#endif
+#ifndef GPUB_DMMA_DKT32
+#define GPUB_DMMA_DKT32 0
+#endif
 #ifndef GPUB_SGEMM64_TN
 #define GPUB_SGEMM64_TN 8
 #endif
@@ -1015,15 +1023,20 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
         const bool ok = (m % 64 == 0) && (n % 64 == 0) && (k % DK == 0) && k >= DK && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         ((((uintptr_t) A) | ((uintptr_t) B)) % 16 == 0) && (sA % 2 == 0) && (sB % 2 == 0);
         if (ok) {
-            if (false && k % 32 == 0) {   // measured: 32-deep panels are 2 % slower than 16-deep ones on 128^3 (profiles/r1e)
+            if (GPUB_DMMA_DKT32 && k % 32 == 0) {   // measured: 32-deep panels are 2 % slower than 16-deep ones on 128^3 (profiles/r1e)
                 constexpr size_t smem32 = sizeof(double) * (2 * 32 * DLD + 2 * 64 * (32 + 4));
-                GPUB_CUDA(cudaFuncSetAttribute(k_gemm_dmma<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem32));
-                k_gemm_dmma<false, 32><<<grid, 256, smem32, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+                GPUB_CUDA(cudaFuncSetAttribute(k_gemm_dmma<false, 32, GPUB_DMMA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem32));
+                k_gemm_dmma<false, 32, GPUB_DMMA_WARPS><<<grid, 32 * GPUB_DMMA_WARPS, smem32, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
                                                                       ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
             } else {
                 constexpr size_t smem16 = sizeof(double) * (2 * 16 * DLD + 2 * 64 * (16 + 4));
+#if GPUB_DMMA_WARPS == 4
+                k_gemm_dmma<false, 16, 4><<<grid, 128, smem16, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
+                                                                         ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+#else
                 k_gemm_dmma<false, 16><<<grid, 256, smem16, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
                                                                       ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
+#endif
             }
             done = true;
         }
