@@ -363,7 +363,9 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // panel then lands as [kk][col] like A's and its fragments are read with A's conflict-free pattern (P = N N^T).
 // DKT: depth of a K panel (16 or 32; 32 halves the number of CTA barriers per tile and needs dynamic shared memory)
 // WARPS: 8 warps of 16 x 32 warp tiles (6 fragment loads per 8 DMMA) or 4 warps of 32 x 32 (8 per 16)
-template<bool TRB, int DKT, int WARPS = 8>
+// SYM (with TRB, A == B): C = A A^T is symmetric -- only the tiles on and below the diagonal are computed, each off-diagonal tile is
+// stored twice (itself and mirrored), which halves the flops of the Nullspace projector N N^T
+template<bool TRB, int DKT, int WARPS = 8, bool SYM = false>
 __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
@@ -377,10 +379,19 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
     constexpr int NTH = 32 * WARPS, WM = WARPS == 8 ? 16 : 32, MI = WM / 8, WR = 64 / WM;
     const int wr = (warp % WR) * WM, wc = (warp / WR) * 32; // warp origin inside the tile
     const int g = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
-    const size_t tiles = tiles_m * tiles_n;
+    const size_t tiles = SYM ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
     for (size_t t = blockIdx.x; t < tiles * batch; t += gridDim.x) {
         const size_t b = t / tiles, r = t - b * tiles;
-        const size_t row0 = (r % tiles_m) * 64, col0 = (r / tiles_m) * 64;
+        size_t row0, col0;
+        if (SYM) {   // r enumerates the lower-triangular tiles column by column
+            size_t rr = r, tj = 0;
+            while (rr >= tiles_m - tj) { rr -= tiles_m - tj; tj++; }
+            row0 = (tj + rr) * 64;
+            col0 = tj * 64;
+        } else {
+            row0 = (r % tiles_m) * 64;
+            col0 = (r / tiles_m) * 64;
+        }
         const double *a = A + b * sA + row0;
         const double *bb = B + b * sB + (TRB ? col0 : col0 * ldb);
         double acc[MI][4][2];
@@ -452,6 +463,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
                 } else {
                     *p0 = alpha * acc[i][j][0] + beta * (*p0);
                     *p1 = alpha * acc[i][j][1] + beta * (*p1);
+                }
+                if (SYM && row0 != col0) {   // the mirrored tile (beta == 0 on this path)
+                    c[gc + gr * ldc] = alpha * acc[i][j][0];
+                    c[gc + 1 + gr * ldc] = alpha * acc[i][j][1];
                 }
             }
     }
@@ -1069,9 +1084,9 @@ template<typename T> bool try_aat_dmma(gpub_ctx_t, cudaStream_t, size_t, const T
 template<>
 bool try_aat_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *N, size_t sN, double *P, size_t sP, size_t batch) {
     if (n % 64 != 0 || (sN & 1) || (((uintptr_t) N) & 15u)) return false;
-    const size_t tm = n / 64, total = tm * tm * batch, cap = (size_t) ctx->sm_count * 8;
+    const size_t tm = n / 64, total = tm * (tm + 1) / 2 * batch, cap = (size_t) ctx->sm_count * 8;
     constexpr size_t smemT = sizeof(double) * (2 * 16 * DLD + 2 * 16 * DLD);
-    k_gemm_dmma<true, 16><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
+    k_gemm_dmma<true, 16, 8, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
     return true;
 }
 

@@ -299,6 +299,22 @@ def test_nullspace_pack_and_projector(gpu_ctx, dt):
     assert not host(dP)[3].any() and not host(dP)[6].any()          # full rank -> exactly zero projector
 
 
+@pytest.mark.parametrize("n,batch", [(64, 5), (192, 3), (256, 2)])
+def test_projector_on_the_tensor_pipe_is_symmetric_and_exact(gpu_ctx, n, batch):
+    """N N^T for n a multiple of 64 (fp64) computes only the tiles on and below the diagonal and mirrors the rest."""
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(n)
+    N = rng.uniform(-1, 1, (batch, n, n))
+    N[:, :, n - n // 8:] = 0.0                        # the zero padding of a left-packed nullspace basis
+    dN = dev(N); dP = torch.full_like(dN, float("nan"))
+    gpu_ctx.call("aat_batched", dN, n, capi._p(dN), n * n, capi._p(dP), n * n, batch)
+    P = host(dP)
+    Nm = host(dN)
+    assert np.array_equal(P, P.transpose(0, 2, 1)), "mirrored tiles must be bit-identical"
+    assert rel_err(P, Nm @ Nm.transpose(0, 2, 1)) <= TOL[np.dtype(np.float64)]
+
+
 def test_generators_match_the_numpy_mirror(gpu_ctx, oracle):
     import torch
     from gputils_b200 import capi
