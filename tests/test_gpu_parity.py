@@ -95,7 +95,7 @@ def test_potrf_potrs(gpu_ctx, oracle, dt, n, batch):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("n", [3, 8, 32, 40, 96, 128])
+@pytest.mark.parametrize("n", [3, 4, 8, 32, 40, 96, 128])
 def test_potrf_reports_first_bad_pivot(gpu_ctx, oracle, dt, n):
     import torch
     from gputils_b200 import capi
