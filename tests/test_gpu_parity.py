@@ -326,20 +326,34 @@ def test_generators_match_the_numpy_mirror(gpu_ctx, oracle):
     assert rel_err(host(A), oracle.fill_spd_batched(8, 5, 8.0, 99)) <= 1e-15
 
 
-def test_padded_strides_are_accepted(gpu_ctx, oracle):
-    """The C ABI takes explicit leading dimensions and batch strides (128-byte aligned padded layouts)."""
+@pytest.mark.parametrize("n,batch,ld,pad", [(5, 11, 8, 8), (4, 9, 6, 4), (30, 7, 32, 0), (50, 5, 52, 12), (64, 3, 66, 2),
+                                            (100, 4, 104, 16), (128, 3, 130, 6)])
+def test_padded_strides_are_accepted(gpu_ctx, oracle, n, batch, ld, pad):
+    """The C ABI takes explicit leading dimensions and batch strides (e.g. 128-byte aligned padded layouts): every size
+    class of the Cholesky kernels (lane groups, warp per matrix, pipelined 32 x 32 blocks) factorises and solves in a padded
+    buffer and leaves the padding untouched."""
     import torch
     from gputils_b200 import capi
-    n, batch, ld, stride = 5, 11, 8, 48          # ld 8, 48 doubles = 384 B per matrix
-    A = oracle.fill_spd_batched(n, batch, 5.0, 3)
+    stride = ld * n + pad
+    A = oracle.fill_spd_batched(n, batch, float(n), 3)
+    b = oracle.fill_uniform(batch * n, -1.0, 1.0, 4).reshape(batch, n, 1)
     buf = torch.full((batch, stride), 777.0, dtype=torch.float64, device="cuda")
     for i in range(batch):
         buf[i, : ld * n].view(n, ld)[:, :n] = torch.from_numpy(A[i].T.copy()).cuda()
     info = torch.zeros(batch, dtype=torch.int32, device="cuda")
     gpu_ctx.call("potrf_batched", buf, n, capi._p(buf), ld, stride, capi._p(info), batch)
+    assert not info.cpu().numpy().any()
     Lo, _ = oracle.potrf_batched(A)
     out = buf.cpu().numpy()
     for i in range(batch):
         L = out[i, : ld * n].reshape(n, ld)[:, :n].T
-        assert rel_err(np.tril(L), np.tril(Lo[i])) <= 1e-13
+        assert rel_err(np.tril(L), np.tril(Lo[i])) <= 1e-12
+        assert np.array_equal(np.triu(L, 1), np.triu(A[i], 1))
         assert np.all(out[i, ld * n:] == 777.0) and np.all(out[i, : ld * n].reshape(n, ld)[:, n:] == 777.0)
+    sb = n + 3
+    rhs = torch.full((batch, sb), 555.0, dtype=torch.float64, device="cuda")
+    rhs[:, :n] = torch.from_numpy(b[:, :, 0].copy()).cuda()
+    gpu_ctx.call("potrs_batched", buf, n, capi._p(buf), ld, stride, capi._p(rhs), sb, batch)
+    x = rhs.cpu().numpy()
+    assert rel_err(x[:, :n, None], oracle.potrs_batched(Lo, b)) <= 2e-11
+    assert np.all(x[:, n:] == 555.0)
