@@ -605,6 +605,9 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 // after the __syncwarp that follows the chunk's last column store, a panel warp sleeps in try_wait (acquire) -- no polling loop
 // competing for issue slots and, unlike a flag + __threadfence_block (MEMBAR.CTA in front of the next LDS of the chain, measured
 // 0.86 -> 1.09 ms), nothing on the diagonal warp's dependency chain.
+#ifndef GPUB_PIPE_RCP_PIVOT
+#define GPUB_PIPE_RCP_PIVOT 0
+#endif
 #ifndef GPUB_PIPE_CHUNK
 #define GPUB_PIPE_CHUNK 4
 #endif
@@ -722,10 +725,21 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             if (!(d > T(0)) && bad == 0) bad = j + 1;
+#if GPUB_PIPE_RCP_PIVOT
+                            // next pivot through the reciprocal: d' = a(j+1,j+1) - a(j+1,j)^2 / d leaves the (longer) rsqrt off the
+                            // pivot-to-pivot chain
+                            const T iv = fast_rcp<T>(d), aj = a[j];
+                            const T dn = fma(-(aj * iv), aj, a[j + 1 < 32 ? j + 1 : j]);
+                            const T r = fast_rsqrt<T>(d);
+                            const T l = aj * r;
+                            a[j] = l;
+                            if (j + 1 < 32) d = __shfl_sync(0xffffffffu, dn, j + 1);
+#else
                             const T r = fast_rsqrt<T>(d);
                             const T l = a[j] * r;
                             a[j] = l;
                             if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
+#endif
                             s_d[j][lane] = l;
                             if (lane == j) s_rinv[j] = r;
                             __syncwarp();

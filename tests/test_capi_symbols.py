@@ -41,6 +41,10 @@ def test_version_string_and_argument_errors_without_gpu():
     # null context is rejected before any CUDA call
     assert lib.gpub_ctx_sync(None, 0) == -1
     assert lib.gpub_ctx_device(None) == -1
+    # multi-GPU plumbing: argument errors before any CUDA or NCCL call, nothing to release
+    assert lib.gpub_multi_allgather(None, 2, 0, None, None, None, 0, None) == -1
+    assert lib.gpub_multi_enable_peer_access(None, 0, None) == -1
+    assert lib.gpub_multi_release() == 0
 
 
 def test_header_cites_reference_lines():
