@@ -605,6 +605,8 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 // after the __syncwarp that follows the chunk's last column store, a panel warp sleeps in try_wait (acquire) -- no polling loop
 // competing for issue slots and, unlike a flag + __threadfence_block (MEMBAR.CTA in front of the next LDS of the chain, measured
 // 0.86 -> 1.09 ms), nothing on the diagonal warp's dependency chain.
+// GPUB_PIPE_RCP_PIVOT = 1 carries the pivots through a reciprocal (the rsqrt leaves the pivot-to-pivot chain). Measured slower
+// (n = 128 fp64 0.78 -> 0.84 ms): the diagonal warp is bound by its instruction count, not by the chain latency.
 #ifndef GPUB_PIPE_RCP_PIVOT
 #define GPUB_PIPE_RCP_PIVOT 0
 #endif
