@@ -9,14 +9,14 @@ rng = np.random.default_rng(0)
 def spd(n, k, dt):
     G = rng.uniform(-1, 1, (k, n, n)); return (G @ G.transpose(0, 2, 1) + n * np.eye(n)).astype(dt)
 for dt in (np.float64, np.float32):
-    for n, k in [(8, 40), (32, 9), (64, 5), (100, 3), (128, 3)]:
+    for n, k in [(4, 300), (8, 40), (16, 20), (32, 9), (64, 5), (100, 3), (128, 3)]:
         A = capi.from_numpy_batch(spd(n, k, dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (k, n, 1)).astype(dt))
         info = torch.zeros(k, dtype=torch.int32, device="cuda")
         capi.potrf_batched(ctx, A, info); capi.potrs_batched(ctx, A, b)
     for (m, n, kk, k) in [(8, 8, 8, 50), (32, 32, 32, 9), (64, 64, 64, 3), (128, 128, 128, 2), (256, 1, 256, 3), (100, 1, 70, 3)]:
         A = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, kk)).astype(dt)); B = capi.from_numpy_batch(rng.uniform(-1, 1, (k, kk, n)).astype(dt))
         Cm = torch.zeros((k, n, m), dtype=A.dtype, device="cuda"); capi.gemm_batched(ctx, Cm, A, B)
-    A = capi.from_numpy_batch(rng.uniform(-1, 1, (9, 64, 16)).astype(dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (9, 64, 1)).astype(dt))
+    A = capi.from_numpy_batch(rng.uniform(-1, 1, (69, 64, 16)).astype(dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (69, 64, 1)).astype(dt))
     capi.gels_batched(ctx, A, b)
 for (m, n, k) in [(1024, 128, 2), (300, 40, 2), (513, 38, 1)]:
     A = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, n))); tau = torch.zeros((k, n), dtype=torch.float64, device="cuda")
