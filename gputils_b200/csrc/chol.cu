@@ -605,10 +605,10 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 // after the __syncwarp that follows the chunk's last column store, a panel warp sleeps in try_wait (acquire) -- no polling loop
 // competing for issue slots and, unlike a flag + __threadfence_block (MEMBAR.CTA in front of the next LDS of the chain, measured
 // 0.86 -> 1.09 ms), nothing on the diagonal warp's dependency chain.
-// GPUB_PIPE_RCP_PIVOT = 1 carries the pivots through a reciprocal (the rsqrt leaves the pivot-to-pivot chain). Measured slower
-// (n = 128 fp64 0.78 -> 0.84 ms): the diagonal warp is bound by its instruction count, not by the chain latency.
-#ifndef GPUB_PIPE_RCP_PIVOT
-#define GPUB_PIPE_RCP_PIVOT 0
+// Measured and rejected in the diagonal loop (n = 128 fp64 0.78 -> 0.84 ms): pivots carried through a reciprocal so that the rsqrt
+// leaves the pivot-to-pivot chain -- the diagonal warp is bound by its instruction count, not by the chain latency.
+#ifndef GPUB_DIAG_SPLIT
+#define GPUB_DIAG_SPLIT 1
 #endif
 #ifndef GPUB_PIPE_CHUNK
 #define GPUB_PIPE_CHUNK 4
@@ -724,30 +724,85 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
                     if (rb == hb) { // diagonal block
                         int bad = 0;
                         T d = __shfl_sync(0xffffffffu, a[0], 0);
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
+                        // One column: pivot -> rsqrt -> scale -> publish -> update of the columns j < c < CEND. The diagonal warp runs alone
+                        // and is bound by its instruction count, so with SPLIT (fp64) the columns 0..15 update only the columns up to 15; the
+                        // rank-16 update they owe to the lower-right 16 x 16 corner is then done at once on the tensor pipe (16 DMMA + the
+                        // two layout changes: ~80 instructions instead of 256 DFMA + 128 LDS), and the columns 16..31 follow as before.
+                        constexpr bool SPLIT = FRAG && GPUB_DIAG_SPLIT;
+                        auto column = [&](auto jt, auto cendt) {
+                            constexpr int j = decltype(jt)::value, CEND = decltype(cendt)::value;
                             if (!(d > T(0)) && bad == 0) bad = j + 1;
-#if GPUB_PIPE_RCP_PIVOT
-                            // next pivot through the reciprocal: d' = a(j+1,j+1) - a(j+1,j)^2 / d leaves the (longer) rsqrt off the
-                            // pivot-to-pivot chain
-                            const T iv = fast_rcp<T>(d), aj = a[j];
-                            const T dn = fma(-(aj * iv), aj, a[j + 1 < 32 ? j + 1 : j]);
-                            const T r = fast_rsqrt<T>(d);
-                            const T l = aj * r;
-                            a[j] = l;
-                            if (j + 1 < 32) d = __shfl_sync(0xffffffffu, dn, j + 1);
-#else
                             const T r = fast_rsqrt<T>(d);
                             const T l = a[j] * r;
                             a[j] = l;
-                            if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
-#endif
+                            if (j + 1 < CEND) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
                             s_d[j][lane] = l;
                             if (lane == j) s_rinv[j] = r;
                             __syncwarp();
                             if ((j + 1) % GPUB_PIPE_CHUNK == 0 && lane == 0) chol_mbar_arrive(&s_bar[j / GPUB_PIPE_CHUNK]);
 #pragma unroll
-                            for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+                            for (int c = j + 1; c < CEND; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+                        };
+                        auto columns = [&](auto j0t, auto cendt) {   // 16 columns starting at j0, explicit constants keep a[] in registers
+                            constexpr int J0 = decltype(j0t)::value;
+#define GPUB_COL(K) column(std::integral_constant<int, J0 + K>{}, cendt);
+                            GPUB_COL(0) GPUB_COL(1) GPUB_COL(2) GPUB_COL(3) GPUB_COL(4) GPUB_COL(5) GPUB_COL(6) GPUB_COL(7)
+                            GPUB_COL(8) GPUB_COL(9) GPUB_COL(10) GPUB_COL(11) GPUB_COL(12) GPUB_COL(13) GPUB_COL(14) GPUB_COL(15)
+#undef GPUB_COL
+                        };
+                        if constexpr (SPLIT) {
+                            columns(std::integral_constant<int, 0>{}, std::integral_constant<int, 16>{});
+                            // corner (rows, columns 16..31) -= L21 L21^T with L21 = rows 16..31 of the columns just published in s_d
+                            T *scr = &s_p[hb & 1][hb][0][0];   // the diagonal block row has no panel slot of its own: free scratch
+                            if (lane >= 16) {
+#pragma unroll
+                                for (int c = 0; c < 16; c++) scr[c * LDP + lane - 16] = a[16 + c];
+                            }
+                            __syncwarp();
+                            double cf[2][2][2];
+#pragma unroll
+                            for (int i = 0; i < 2; i++)
+#pragma unroll
+                                for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                                    for (int e = 0; e < 2; e++) cf[i][jj][e] = (double) scr[(8 * jj + 2 * q + e) * LDP + 8 * i + g];
+#pragma unroll
+                            for (int k4 = 0; k4 < 16; k4 += 4) {
+                                const double f0 = (double) s_d[k4 + q][16 + g], f1 = (double) s_d[k4 + q][24 + g];
+                                chol_dmma(cf[0][0][0], cf[0][0][1], -f0, f0);
+                                chol_dmma(cf[0][1][0], cf[0][1][1], -f0, f1);
+                                chol_dmma(cf[1][0][0], cf[1][0][1], -f1, f0);
+                                chol_dmma(cf[1][1][0], cf[1][1][1], -f1, f1);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 2; i++)
+#pragma unroll
+                                for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                                    for (int e = 0; e < 2; e++) scr[(8 * jj + 2 * q + e) * LDP + 8 * i + g] = (T) cf[i][jj][e];
+                            __syncwarp();
+                            if (lane >= 16) {
+#pragma unroll
+                                for (int c = 0; c < 16; c++) a[16 + c] = scr[c * LDP + lane - 16];
+                            }
+                            d = __shfl_sync(0xffffffffu, a[16], 16);
+                            columns(std::integral_constant<int, 16>{}, std::integral_constant<int, 32>{});
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (!(d > T(0)) && bad == 0) bad = j + 1;
+                                const T r = fast_rsqrt<T>(d);
+                                const T l = a[j] * r;
+                                a[j] = l;
+                                if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
+                                s_d[j][lane] = l;
+                                if (lane == j) s_rinv[j] = r;
+                                __syncwarp();
+                                if ((j + 1) % GPUB_PIPE_CHUNK == 0 && lane == 0) chol_mbar_arrive(&s_bar[j / GPUB_PIPE_CHUNK]);
+#pragma unroll
+                                for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
+                            }
                         }
                         if (lane == 0 && bad != 0) atomicCAS(&s_bad, 0, 32 * hb + bad);
                     } else { // panel block: one column behind the diagonal warp
@@ -1293,6 +1348,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
                 pair64_forward<T>(lo, hi, xlo, xhi);
                 s_x[p] = xlo;
                 s_x[p + 32] = xhi;
+                __syncwarp();                  // lanes that loaded different row counts reconverge before the aligned CTA barrier
                 __syncthreads();               // (1) y1 published
                 __syncthreads();               // (2) warps 1, 2 have updated the second right-hand side
                 __syncthreads();               // (3) v2 published
@@ -1305,6 +1361,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
             } else {
                 s_x[64 + p] = xlo;             // scaled rhs of block 2, updated by warps 1, 2 after barrier (1)
                 s_x[96 + p] = xhi;
+                __syncwarp();
                 __syncthreads();               // (1)
                 __syncthreads();               // (2)
                 xlo = s_x[64 + p];
@@ -1315,6 +1372,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
                 s_x[96 + p] = xhi;
                 if (p < nloc) b_g[64 + p] = xlo * ilo;
                 if (p + 32 < nloc) b_g[96 + p] = xhi * ihi;
+                __syncwarp();
                 __syncthreads();               // (3)
                 __syncthreads();               // (4)
             }
@@ -1328,6 +1386,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
             const T idg = ok ? T(1) / l_g[row + (size_t) row * ldl] : T(1);
 #pragma unroll
             for (int c = 0; c < 64; c++) r[c] *= idg;
+            __syncwarp();
             __syncthreads();                   // (1) y1 published
             T t0 = 0, t1 = 0;
 #pragma unroll
