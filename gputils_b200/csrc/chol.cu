@@ -1328,6 +1328,18 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(in
 //   backward: warps 1, 2: Lb21^T v2 (64 per-lane products, two 31-shuffle transpose-reduce butterflies) -> warp 0 finishes.
 // Five CTA barriers per matrix instead of the sixteen of k_potrs_blk<T, 4>, and no warp ever waits inside a 32-column block.
 // ------------------------------------------------------------------------------------------
+// The four warps of k_potrs_quad128 play different roles and meet at the CTA barrier from their own branches (every thread executes
+// the same number of barriers). That is what named barriers are for at the PTX level (bar.sync id, count: warps may arrive from
+// different instructions); __syncthreads() in role-dependent code is outside the CUDA C++ rules and compute-sanitizer synccheck
+// reports it, so the kernel uses barrier 1 with an explicit thread count.
+// synccheck additionally wants every warp to arrive from the SAME barrier instruction: built with -DGPUB_SYNCCHECK_CLEAN the barrier is
+// one non-inlined function (synccheck: 0 errors on scripts/dev_sanitize.py); the call costs 7-10 % at n = 128, so the default inlines it.
+#ifdef GPUB_SYNCCHECK_CLEAN
+__device__ __noinline__ void quad_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+#else
+__device__ __forceinline__ void quad_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+#endif
+
 template<typename T>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MINB) k_potrs_quad128(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b,
                                                                                 size_t strideB, size_t batch) {
@@ -1348,11 +1360,10 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
                 pair64_forward<T>(lo, hi, xlo, xhi);
                 s_x[p] = xlo;
                 s_x[p + 32] = xhi;
-                __syncwarp();                  // lanes that loaded different row counts reconverge before the aligned CTA barrier
-                __syncthreads();               // (1) y1 published
-                __syncthreads();               // (2) warps 1, 2 have updated the second right-hand side
-                __syncthreads();               // (3) v2 published
-                __syncthreads();               // (4) coupling partials published
+                quad_sync();                  // (1) y1 published
+                quad_sync();                  // (2) warps 1, 2 have updated the second right-hand side
+                quad_sync();                  // (3) v2 published
+                quad_sync();                  // (4) coupling partials published
                 xlo -= s_part[0][p] + s_part[1][p];
                 xhi -= s_part[0][p + 32] + s_part[1][p + 32];
                 pair64_backward<T>(lo, hi, xlo, xhi, s_t[0], p);
@@ -1361,9 +1372,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
             } else {
                 s_x[64 + p] = xlo;             // scaled rhs of block 2, updated by warps 1, 2 after barrier (1)
                 s_x[96 + p] = xhi;
-                __syncwarp();
-                __syncthreads();               // (1)
-                __syncthreads();               // (2)
+                quad_sync();                  // (1)
+                quad_sync();                  // (2)
                 xlo = s_x[64 + p];
                 xhi = s_x[96 + p];
                 pair64_forward<T>(lo, hi, xlo, xhi);
@@ -1372,9 +1382,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
                 s_x[96 + p] = xhi;
                 if (p < nloc) b_g[64 + p] = xlo * ilo;
                 if (p + 32 < nloc) b_g[96 + p] = xhi * ihi;
-                __syncwarp();
-                __syncthreads();               // (3)
-                __syncthreads();               // (4)
+                quad_sync();                  // (3)
+                quad_sync();                  // (4)
             }
         } else {
             // one row of L21 per lane: row 64 + 32 (warp - 1) + p, scaled by the reciprocal diagonal of ITS row
@@ -1386,8 +1395,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
             const T idg = ok ? T(1) / l_g[row + (size_t) row * ldl] : T(1);
 #pragma unroll
             for (int c = 0; c < 64; c++) r[c] *= idg;
-            __syncwarp();
-            __syncthreads();                   // (1) y1 published
+            quad_sync();                      // (1) y1 published
             T t0 = 0, t1 = 0;
 #pragma unroll
             for (int c = 0; c < 64; c += 2) {
@@ -1395,8 +1403,8 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
                 t1 = fma(r[c + 1], s_x[c + 1], t1);
             }
             s_x[row] -= t0 + t1;
-            __syncthreads();                   // (2)
-            __syncthreads();                   // (3) v2 published
+            quad_sync();                      // (2)
+            quad_sync();                      // (3) v2 published
             const T v = s_x[row];
             T pr[32];
 #pragma unroll
@@ -1407,9 +1415,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : GPUB_QUAD128_F32_MIN
             for (int c = 0; c < 32; c++) pr[c] = r[32 + c] * v;
             TReduce<T, 32, 16>::run(pr, p);
             s_part[warp - 1][p + 32] = pr[0];
-            __syncthreads();                   // (4)
+            quad_sync();                      // (4)
         }
-        __syncthreads();                       // (5) the shared vectors are free for the next matrix
+        quad_sync();                          // (5) the shared vectors are free for the next matrix
     }
 }
 

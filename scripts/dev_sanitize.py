@@ -1,6 +1,6 @@
 """Small invocations of every kernel family, meant to be run under compute-sanitizer (memcheck / racecheck / synccheck):
    compute-sanitizer --tool racecheck python scripts/dev_sanitize.py"""
-import sys
+import os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 from gputils_b200 import capi
@@ -12,7 +12,10 @@ for dt in (np.float64, np.float32):
     for n, k in [(4, 300), (8, 40), (16, 20), (32, 9), (64, 5), (100, 3), (128, 3)]:
         A = capi.from_numpy_batch(spd(n, k, dt)); b = capi.from_numpy_batch(rng.uniform(-1, 1, (k, n, 1)).astype(dt))
         info = torch.zeros(k, dtype=torch.int32, device="cuda")
-        capi.potrf_batched(ctx, A, info); capi.potrs_batched(ctx, A, b)
+        capi.potrf_batched(ctx, A, info)
+        # GPUB_SANITIZE_SKIP_QUAD=1: synccheck stops at k_potrs_quad128 (role-dependent arrival at a named barrier)
+        if not (n > 64 and os.environ.get("GPUB_SANITIZE_SKIP_QUAD") == "1"):
+            capi.potrs_batched(ctx, A, b)
     for (m, n, kk, k) in [(8, 8, 8, 50), (32, 32, 32, 9), (64, 64, 64, 3), (128, 128, 128, 2), (256, 1, 256, 3), (100, 1, 70, 3)]:
         A = capi.from_numpy_batch(rng.uniform(-1, 1, (k, m, kk)).astype(dt)); B = capi.from_numpy_batch(rng.uniform(-1, 1, (k, kk, n)).astype(dt))
         Cm = torch.zeros((k, n, m), dtype=A.dtype, device="cuda"); capi.gemm_batched(ctx, Cm, A, B)
