@@ -30,7 +30,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(REPO / "include"), "-I", str(CSRC)]
 # per-file extra flags: the LAPACK-faithful SVD core must round exactly like its host build
 EXTRA = {"svd.cu": ["--fmad=false"]}
-SOURCES = ["ctx.cu", "blas1.cu", "gemm.cu", "chol.cu", "qr.cu", "svd.cu", "multi.cu"]
+SOURCES = ["ctx.cu", "mem.cu", "blas1.cu", "gemm.cu", "chol.cu", "qr.cu", "svd.cu", "multi.cu"]
 
 
 def nvcc() -> str:

@@ -51,6 +51,7 @@ _TYPED = {
     "aat_batched": [_sz, _vp, _sz, _vp, _sz, _sz],
     "fill_uniform": [_sz, _vp, "T", "T", _u64],
     "fill_spd_batched": [_sz, _vp, _sz, "T", _u64, _sz],
+    "chol_solve_from_host": [_sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz],
 }
 
 #: every symbol include/gputils_b200.h declares (checked by tests/test_capi_symbols.py)
@@ -58,7 +59,8 @@ EXPORTED = (
     ["gpub_version", "gpub_ctx_get", "gpub_ctx_ensure_streams", "gpub_ctx_num_streams", "gpub_ctx_stream",
      "gpub_ctx_bind_stream", "gpub_ctx_sync", "gpub_ctx_sync_all", "gpub_ctx_release", "gpub_ctx_release_all", "gpub_ctx_device", "gpub_ctx_sm_count",
      "gpub_multi_device_count", "gpub_multi_enable_peer_access", "gpub_multi_nccl_version", "gpub_multi_allgather", "gpub_multi_release",
-     "gpub_fill_ptr_table", "gpub_gesvd_batched_worksize_f64", "gpub_gesvd_batched_worksize_f32"]
+     "gpub_fill_ptr_table", "gpub_gesvd_batched_worksize_f64", "gpub_gesvd_batched_worksize_f32",
+     "gpub_mem_alloc", "gpub_mem_free", "gpub_mem_stats", "gpub_mem_trim", "gpub_upload", "gpub_download"]
     + [f"gpub_{n}_{s}" for n in _TYPED for s in ("f64", "f32")]
 )
 
@@ -94,6 +96,12 @@ def load() -> C.CDLL:
     lib.gpub_multi_allgather.argtypes = [C.POINTER(_vp), _int, _int, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), _int, C.POINTER(_int)]
     lib.gpub_ctx_sm_count.argtypes = [_vp]
     lib.gpub_fill_ptr_table.argtypes = [_vp, _int, _vp, _sz, _sz, _vp]
+    lib.gpub_mem_alloc.argtypes = [_vp, _sz, C.POINTER(_vp)]
+    lib.gpub_mem_free.argtypes = [_vp]
+    lib.gpub_mem_stats.argtypes = [_vp, C.POINTER(_sz), C.POINTER(_sz)]
+    lib.gpub_mem_trim.argtypes = [_vp, _sz]
+    lib.gpub_upload.argtypes = [_vp, _int, _vp, _vp, _sz]
+    lib.gpub_download.argtypes = [_vp, _int, _vp, _vp, _sz]
     for suf in ("f64", "f32"):
         fn = getattr(lib, f"gpub_gesvd_batched_worksize_{suf}")
         fn.argtypes = [_sz, _sz, _int, _sz]
@@ -255,3 +263,42 @@ def fill_uniform(ctx: Context, x, lo, hi, seed: int):
 def fill_spd_batched(ctx: Context, A, shift, seed: int):
     k, n = A.shape[0], A.shape[1]
     ctx.call("fill_spd_batched", A, n, _p(A), n * n, shift, seed, k)
+
+
+def count_gt_batched(ctx: Context, S, eps: float):
+    """rank_i = #{ j : S_i[j] > eps } (ref: tensor.cuh:1600-1609), one launch; returns int32 (k,)."""
+    import torch
+    k, length = S.shape[0], S.shape[1]
+    count = torch.zeros(k, dtype=torch.int32, device=S.device)
+    ctx.call("count_gt_batched", S, _p(S), length, length, eps, _p(count), k)
+    return count
+
+
+def nullspace_build(ctx: Context, a, eps: float = 1e-6):
+    """The launch sequence of Nullspace<T>::Nullspace (include/gpub200/factorisers.cuh; ref: tensor.cuh:2046-2079) through
+    the C ABI: tr -> gesvd(U) -> rank -> pack -> N N'. `a` is (k, n, m) in DTensor layout, i.e. m x n fat matrices (m <= n).
+    Returns N (k, n, n), the projector N N' (k, n, n) and the ranks."""
+    import torch
+    k, n, m = a.shape
+    assert m <= n
+    at = transpose_batched(ctx, a)                       # n x m tall
+    S, U, _, info = gesvd_batched(ctx, at, True)
+    rank = count_gt_batched(ctx, S, eps)
+    N = torch.empty((k, n, n), dtype=a.dtype, device=a.device)
+    P = torch.empty((k, n, n), dtype=a.dtype, device=a.device)
+    ctx.call("nullspace_pack_batched", a, n, _p(U), n * n, _p(rank), _p(N), n * n, k)
+    ctx.call("aat_batched", a, n, _p(N), n * n, _p(P), n * n, k)
+    return N, P, rank
+
+
+def nullspace_project(ctx: Context, P, b):
+    """b_i <- (N_i N_i') b_i in place: addAB with C aliasing B (ref: tensor.cuh:2081-2085)."""
+    gemm_batched(ctx, b, P, b)
+
+
+def chol_solve_from_host(ctx: Context, A, b, info, A_host, b_host, x_host, info_host, chunks: int = 16, sidx: int = 0):
+    """The product's host pipeline (gpub_chol_solve_from_host_*): upload / factorise + solve / download of successive chunks
+    overlap on three streams. A, b, info are device tensors (k, n, n) / (k, 1, n) / (k,); the host tensors may be pinned."""
+    k, n = A.shape[0], A.shape[1]
+    hp = lambda t: _vp(t.data_ptr()) if t is not None else None
+    ctx.call("chol_solve_from_host", A, n, _p(A), hp(b), hp(info), hp(A_host), hp(b_host), hp(x_host), hp(info_host), k, chunks, sidx=sidx)

@@ -22,12 +22,26 @@ struct gpub_stream_slot {
     size_t big_bytes = 0;
 };
 
+#define GPUB_RING_SLOTS 4
+#define GPUB_RING_CHUNK_BYTES (8ull << 20)
+
 struct gpub_ctx {
     int device = 0;
     int sm_count = 148;
     int max_smem_optin = 0;
     std::deque<gpub_stream_slot> slots;  // deque: growing never moves existing slots
     std::mutex mu;
+    // stream-ordered allocator behind Session::cudaAllocate (gpub_mem_alloc / gpub_mem_free): a context-owned pool whose
+    // release threshold keeps freed blocks cached, so a DTensor constructor / destructor is a pool hit, not a cudaMalloc
+    cudaMemPool_t pool = nullptr;
+    bool pool_tried = false;
+    // host <-> device staging (gpub_upload / gpub_download / gpub_chol_solve_from_host): pinned bounce ring + events,
+    // two private non-blocking streams for the upload / download legs of the host pipeline
+    void *ring[GPUB_RING_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ring_ev[GPUB_RING_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> events;     // cached, timing disabled (host pipeline)
+    std::mutex io_mu;                    // one host transfer at a time per context
 };
 
 #define GPUB_CUDA(expr)                              \
@@ -59,6 +73,14 @@ gpub_stream_slot *gpub_slot(gpub_ctx_t ctx, int sidx, int *err);
 // GPUB_BIG_MAX_BYTES (callers then fall back to a stream-ordered allocation). Growing synchronises the slot's stream.
 #define GPUB_BIG_MAX_BYTES (256ull << 20)
 void *gpub_slot_big(gpub_stream_slot *slot, size_t bytes);
+
+// pageable / pinned host <-> device copies of any size on `stream` (ctx.cu): pinned host memory is DMA'd directly, pageable
+// memory goes through the context's pinned ring in GPUB_RING_CHUNK_BYTES pieces staged by several host threads.
+// H2D returns once the last piece has been QUEUED (the host buffer may be reused); D2H returns once the data is in `dst`.
+int gpub_h2d(gpub_ctx_t ctx, cudaStream_t stream, void *dst_dev, const void *src_host, size_t bytes);
+int gpub_d2h(gpub_ctx_t ctx, cudaStream_t stream, void *dst_host, const void *src_dev, size_t bytes);
+// the two private non-blocking streams of the host pipeline and n cached events
+int gpub_ctx_aux(gpub_ctx_t ctx, cudaStream_t *up, cudaStream_t *down, size_t n_events, cudaEvent_t **events);
 
 #define GPUB_ENTER(ctx, sidx)                              \
     if (!(ctx)) return GPUB_EINVAL;                        \

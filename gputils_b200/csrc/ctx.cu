@@ -3,8 +3,11 @@
 // context, each stream with its own reduction scratch and a mapped pinned result slot.
 #include "common.cuh"
 
+#include <algorithm>
 #include <map>
 #include <memory>
+
+int gpub_mem_release(gpub_ctx_t ctx);   // mem.cu: pinned ring, aux streams, cached events, memory pool
 
 namespace {
 std::mutex g_registry_mu;
@@ -163,6 +166,7 @@ int gpub_ctx_release(gpub_ctx_t ctx) {
         if (s.stream && s.owned) keep(cudaStreamDestroy(s.stream));
         s = gpub_stream_slot();   // recreated lazily if the slot is used again
     }
+    keep((cudaError_t) std::max(gpub_mem_release(ctx), 0));
     return first_err;
 }
 

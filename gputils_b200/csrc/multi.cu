@@ -13,6 +13,8 @@
 #include <set>
 #include <string>
 
+int gpub_mem_pool_allow_peer(gpub_ctx_t ctx, int peer_device);   // mem.cu
+
 namespace {
 
 // the handful of NCCL entry points used, declared locally so that no NCCL header is needed at build time
@@ -85,7 +87,13 @@ std::vector<ncclComm_t> *clique(const gpub_ctx_t *ctxs, int n) {
 int gather_p2p(const gpub_ctx_t *ctxs, int n, int sidx, const void *const *send, const size_t *bytes, void *const *recv) {
     // every destination device pulls the n shards into its receive buffer on its own stream; a source shard must be complete
     // first, so the destination stream waits on an event recorded on the source stream
-    std::vector<cudaEvent_t> ready(n, nullptr);
+    struct Events {                                     // destroyed on every exit path (destruction is deferred by the
+        std::vector<cudaEvent_t> v;                     // runtime until the event has completed)
+        explicit Events(int n) : v(n, nullptr) {}
+        ~Events() { for (auto e: v) if (e) cudaEventDestroy(e); }
+        cudaEvent_t &operator[](int i) { return v[i]; }
+    };
+    Events ready(n), done(n);
     std::vector<cudaStream_t> streams(n, nullptr);
     for (int g = 0; g < n; g++) {
         gpub_device_guard guard(ctxs[g]->device);
@@ -112,7 +120,6 @@ int gather_p2p(const gpub_ctx_t *ctxs, int n, int sidx, const void *const *send,
     }
     // a source buffer may be reused by its owner as soon as every destination has read it: the owner's stream waits for all
     // the copies (events recorded after the copies on the destination streams)
-    std::vector<cudaEvent_t> done(n, nullptr);
     for (int g = 0; g < n && rc == GPUB_OK; g++) {
         gpub_device_guard guard(ctxs[g]->device);
         cudaError_t e = cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
@@ -123,10 +130,6 @@ int gather_p2p(const gpub_ctx_t *ctxs, int n, int sidx, const void *const *send,
         gpub_device_guard guard(ctxs[g]->device);
         for (int r = 0; r < n; r++)
             if (r != g && done[r]) cudaStreamWaitEvent(streams[g], done[r], 0);
-    }
-    for (int g = 0; g < n; g++) {
-        if (ready[g]) cudaEventDestroy(ready[g]);   // destruction is deferred by the runtime until the event has completed
-        if (done[g]) cudaEventDestroy(done[g]);
     }
     return rc;
 }
@@ -157,6 +160,12 @@ int gpub_multi_enable_peer_access(const int *devices, int n, int *n_pairs_enable
                 e = cudaSuccess;
             }
             GPUB_CUDA(e);
+            // tensors come out of the context's memory pool: pool memory needs its own grant for the peer
+            gpub_ctx_t peer_ctx = nullptr;
+            int pe = gpub_ctx_get(devices[j], &peer_ctx);
+            if (pe) return pe;
+            pe = gpub_mem_pool_allow_peer(peer_ctx, devices[i]);
+            if (pe) return pe;
             pairs++;
         }
     }

@@ -359,10 +359,22 @@ template<> int internal_ormqr<float>(gpub_ctx_t c, int s, int tr, size_t m, size
 
 inline size_t per_matrix_work_elems(size_t n) { return 2 * n * n + 8 * n + 8; }
 
+// shared memory of the Jacobi kernel for an n x n factor (sm_100a: 227 KB opt-in per CTA, 2 KB kept for the static part)
+template<typename T>
+inline size_t jacobi_smem(size_t n) { return (n * (n | 1) + 2 * n) * sizeof(T) + n * sizeof(int) + 64; }
+
+template<typename T>
+inline bool shape_supported(size_t m, size_t n) {
+    if (m < n) return false;
+    if (n <= 32) return true;
+    return n <= 256 && jacobi_smem<T>(n) <= (size_t) 227 * 1024 - 2048;
+}
+
+// 0 = shape not served by the batched kernels (the header turns that into std::invalid_argument in the Svd constructor)
 template<typename T>
 size_t worksize(size_t m, size_t n, int jobu, size_t batch) {
-    (void) m;
     (void) jobu;
+    if (!shape_supported<T>(m, n)) return 0;
     return per_matrix_work_elems(n) * batch * sizeof(T) + 256;
 }
 
@@ -374,6 +386,7 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
     if (!want_u && !(jobu == 'N' || jobu == 'n')) return GPUB_EINVAL;
     if (!A || !S || !Vt || (want_u && !U) || !work) return GPUB_EINVAL;
     if (m < n || lda < m || ldvt < n || (want_u && ldu < m)) return GPUB_EINVAL;
+    if (!shape_supported<T>(m, n)) return GPUB_ENOTSUP;
     if (work_bytes < worksize<T>(m, n, jobu, batch)) return GPUB_EWORK;
     GPUB_ENTER(ctx, sidx);
     T *w = reinterpret_cast<T *>((((uintptr_t) work) + 15) & ~(uintptr_t) 15);

@@ -241,11 +241,22 @@ public:
     }
 #endif
 
-    /** cudaMalloc wrapper that counts the bytes handed out. */
+    /**
+     * Device allocation that counts the bytes handed out. The reference calls cudaMalloc here (tensor.cuh:203-210); this takes
+     * the block from the stream-ordered pool of the current device's context (gpub_mem_alloc: ordered on the legacy default
+     * stream, so it is an ordering point for all the Session's blocking streams like cudaMalloc was, without stopping the host;
+     * freed blocks stay cached). Release with Session::cudaRelease (or cudaFree, which also accepts pool memory).
+     */
     cudaError_t cudaAllocate(void **d, size_t s) {
-        cudaError_t err = cudaMalloc(d, s);
-        if (err == cudaSuccess) m_bytesAllocated += s;
-        return err;
+        const int st = gpub_mem_alloc(contextOfCurrentDevice(), s, d);
+        if (st == GPUB_OK) m_bytesAllocated += s;
+        return st >= 0 ? static_cast<cudaError_t>(st) : cudaErrorInvalidValue;
+    }
+
+    /** Returns a block obtained from cudaAllocate to its pool (additive API; the byte counter is the caller's business). */
+    cudaError_t cudaRelease(void *d) {
+        const int st = gpub_mem_free(d);
+        return st >= 0 ? static_cast<cudaError_t>(st) : cudaErrorInvalidValue;
     }
 
     size_t totalAllocatedBytes() const { return m_bytesAllocated; }
@@ -297,6 +308,7 @@ template<typename T> struct Abi;
         static constexpr auto count_gt = gpub_count_gt_batched_##SUF;                                               \
         static constexpr auto nullspace_pack = gpub_nullspace_pack_batched_##SUF;                                   \
         static constexpr auto aat = gpub_aat_batched_##SUF;                                                         \
+        static constexpr auto chol_from_host = gpub_chol_solve_from_host_##SUF;                                     \
     };
 GPUB200_ABI(float, f32)
 GPUB200_ABI(double, f64)

@@ -46,13 +46,13 @@ private:
 
     void destroy() {
         if (m_doDestroyData) {
-            if (m_d_data) gpuErrChk(cudaFree(m_d_data));
+            if (m_d_data) gpuErrChk(Session::getInstance().cudaRelease(m_d_data));
             m_d_data = nullptr;
             Session::getInstance().adjustAllocatedBytes(-static_cast<long long>(bytes()));
             m_doDestroyData = false;
         }
         if (m_doDestroyPtrMatrices) {
-            if (m_d_ptrMatrices) gpuErrChk(cudaFree(m_d_ptrMatrices));
+            if (m_d_ptrMatrices) gpuErrChk(Session::getInstance().cudaRelease(m_d_ptrMatrices));
             m_d_ptrMatrices = nullptr;
             Session::getInstance().adjustAllocatedBytes(-static_cast<long long>(m_numMats * sizeof(T *)));
             m_doDestroyPtrMatrices = false;
@@ -208,12 +208,13 @@ inline void DTensor<T>::allocateOnDevice(size_t size, bool zero) {
     const size_t nbytes = size * sizeof(T);
     gpuErrChk(Session::getInstance().cudaAllocate(reinterpret_cast<void **>(&m_d_data), nbytes));
     m_doDestroyData = true;
-    if (zero) gpuErrChk(cudaMemset(m_d_data, 0, nbytes));
+    /* on the legacy stream, like the allocation: ordered against every blocking stream, asynchronous to the host */
+    if (zero) gpuErrChk(cudaMemsetAsync(m_d_data, 0, nbytes, cudaStreamLegacy));
     if (m_numMats > 1) {
         cudaError_t st = Session::getInstance().cudaAllocate(reinterpret_cast<void **>(&m_d_ptrMatrices),
                                                              m_numMats * sizeof(T *));
         if (st != cudaSuccess) {
-            gpuErrChk(cudaFree(m_d_data));
+            gpuErrChk(Session::getInstance().cudaRelease(m_d_data));
             gpuErrChk(st);
         }
         m_doDestroyPtrMatrices = true;
@@ -249,7 +250,7 @@ DTensor<T>::DTensor(const DTensor<T> &other)
     : m_numRows(other.m_numRows), m_numCols(other.m_numCols), m_numMats(other.m_numMats),
       m_idxStream(other.m_idxStream) {
     allocateOnDevice(numEl());
-    if (numEl() > 0) gpuErrChk(cudaMemcpy(m_d_data, other.raw(), bytes(), cudaMemcpyDeviceToDevice));
+    if (numEl() > 0) gpuErrChk(cudaMemcpyAsync(m_d_data, other.raw(), bytes(), cudaMemcpyDeviceToDevice, cudaStreamLegacy));
     initialisePointersToMatricesData();
 }
 
@@ -315,7 +316,7 @@ void DTensor<T>::reshape(size_t newNumRows, size_t newNumCols, size_t newNumMats
     /* the pointer table is reallocated only when it has to grow */
     if (newNumMats > m_numMats) {
         if (m_d_ptrMatrices && m_doDestroyPtrMatrices) {
-            gpuErrChk(cudaFree(m_d_ptrMatrices));
+            gpuErrChk(Session::getInstance().cudaRelease(m_d_ptrMatrices));
             Session::getInstance().adjustAllocatedBytes(-static_cast<long long>(m_numMats * sizeof(T *)));
         }
         m_d_ptrMatrices = nullptr;
@@ -352,20 +353,37 @@ inline T **DTensor<T>::ptrMatrices() const { return m_d_ptrMatrices; }
 
 /* ------------------------------------------------------------------------------------------------
  *  host <-> device
- *  Synchronous cudaMemcpy, as in the reference: it orders against the blocking streams of the
- *  context, so "after a method returns, a later download observes it" holds across streams.
+ *  Blocking, as in the reference (synchronous cudaMemcpy, tensor.cuh:1128-1154): "after a method returns, a later
+ *  download observes it" holds across streams. gpub_upload / gpub_download queue the copy on the tensor's stream,
+ *  stage pageable host memory through the context's pinned ring with several host threads (the DMA of one 8 MB piece
+ *  overlaps the staging of the next) and return when the data has arrived. A download first joins the other blocking
+ *  streams through the legacy stream, like cudaMemcpy did.
  * ------------------------------------------------------------------------------------------------ */
+
+namespace gpub200 {
+/* makes stream `idx` of the current device's context wait for everything queued on the Session's other blocking streams */
+inline void joinStreams(size_t idx) {
+    if (Session::getInstance().numStreams() <= 1) return;
+    cudaEvent_t ev;
+    gpuErrChk(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    gpuErrChk(cudaEventRecord(ev, cudaStreamLegacy));   /* the legacy stream waits for all blocking streams */
+    gpuErrChk(cudaStreamWaitEvent(Session::getInstance().streamOfCurrentDevice(idx), ev, 0));
+    gpuErrChk(cudaEventDestroy(ev));
+}
+} // namespace gpub200
 
 template<typename T>
 inline bool DTensor<T>::upload(const std::vector<T> &vec, StorageMode mode) {
     if (vec.size() != numEl()) throw std::invalid_argument("[upload] vec has wrong size");
     if (vec.empty()) return true;
+    gpub200::joinStreams(m_idxStream);   /* earlier readers / writers of this tensor on other streams finish first */
     if (mode == StorageMode::rowMajor) {
         std::vector<T> cm(vec.size());
         rm2cm(vec, cm);
-        gpuErrChk(cudaMemcpy(m_d_data, cm.data(), bytes(), cudaMemcpyHostToDevice));
+        gpuErrChk(gpub_upload(gpub200::ctx(), (int) m_idxStream, m_d_data, cm.data(), bytes()));
     } else {
-        gpuErrChk(cudaMemcpy(m_d_data, vec.data(), bytes(), cudaMemcpyHostToDevice));
+        /* no host-side copy of the vector (the reference makes one, tensor.cuh:1134-1139) */
+        gpuErrChk(gpub_upload(gpub200::ctx(), (int) m_idxStream, m_d_data, vec.data(), bytes()));
     }
     return true;
 }
@@ -374,7 +392,8 @@ template<typename T>
 inline void DTensor<T>::download(std::vector<T> &vec) const {
     vec.resize(numEl());
     if (vec.empty()) return;
-    gpuErrChk(cudaMemcpy(vec.data(), m_d_data, bytes(), cudaMemcpyDeviceToHost));
+    gpub200::joinStreams(m_idxStream);
+    gpuErrChk(gpub_download(gpub200::ctx(), (int) m_idxStream, vec.data(), m_d_data, bytes()));
 }
 
 template<typename T>
@@ -617,6 +636,9 @@ template<typename T>
 inline DTensor<T> DTensor<T>::tr() const {
     GPUB200_FP_ONLY(T);
     DTensor<T> transposes(m_numCols, m_numRows, m_numMats);
+    /* the result carries the stream that fills it, so whatever the caller queues on it next is ordered behind the transpose
+     * (the reference hands back a stream-0 tensor filled on stream m_idxStream: Nullspace then mixes two unordered streams) */
+    transposes.m_idxStream = m_idxStream;
     const size_t perMat = m_numRows * m_numCols;
     gpuErrChk(gpub200::Abi<T>::transpose(gpub200::ctx(), (int) m_idxStream, m_numRows, m_numCols, raw(), perMat,
                                          transposes.raw(), perMat, m_numMats));
@@ -628,6 +650,7 @@ inline DTensor<T> DTensor<T>::getRows(size_t rowsFrom, size_t rowsTo, size_t mat
     GPUB200_FP_ONLY(T);
     const size_t len = rowsTo - rowsFrom + 1;
     DTensor<T> rowsOnly(len, m_numCols, 1);
+    rowsOnly.m_idxStream = m_idxStream;
     gpuErrChk(gpub200::Abi<T>::gather_rows(gpub200::ctx(), (int) m_idxStream, raw() + matIdx * m_numRows * m_numCols,
                                            m_numRows, rowsFrom, len, m_numCols, rowsOnly.raw()));
     return rowsOnly;

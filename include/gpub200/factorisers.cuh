@@ -88,6 +88,11 @@ public:
         m_computeU = computeU;
         const size_t m = mat.numRows(), n = mat.numCols(), nMats = mat.numMats();
         computeWorkspaceSize(m, n);
+        /* shapes the batched kernels cannot serve are refused here, as an exception, not at factorise() time as an exit */
+        if (m_lwork == 0 && mat.numEl() > 0) {
+            if (!m_destroyMatrix) delete m_tensor;
+            throw std::invalid_argument("[svd] matrix shape not supported by the batched SVD kernels (see INTEGRATION.md)");
+        }
         m_workspace = std::make_unique<DTensor<unsigned char> >(m_lwork, 1, 1);
         m_Vtr = std::make_shared<DTensor<T> >(n, n, nMats);
         m_S = std::make_shared<DTensor<T> >(std::min(m, n), 1, nMats);
@@ -321,18 +326,18 @@ inline Nullspace<T>::Nullspace(DTensor<T> &a) {
     if (m > n) throw std::invalid_argument("[nullspace] I was expecting a square or fat matrix");
     m_nullspace = std::make_unique<DTensor<T> >(n, n, nMats);
     m_projOp = std::make_unique<DTensor<T> >(n, n, nMats);
-    auto aTranspose = a.tr();
+    auto aTranspose = a.tr();   /* carries a's stream: the whole constructor runs on ONE stream */
     Svd<T> svd(aTranspose, true);
     svd.factorise();
     DTensor<unsigned int> const &devRank = svd.rank();
     std::shared_ptr<DTensor<T> > U = svd.leftSingularVectors().value();
-    const int s = (int) a.streamIdx();
+    const int s = (int) aTranspose.streamIdx();
     /* N_i = last (n - rank_i) columns of U_i, moved to the front, zero elsewhere; then N_i N_i' */
     gpuErrChk(gpub200::Abi<T>::nullspace_pack(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(),
                                               n * n, nMats));
     gpuErrChk(gpub200::Abi<T>::aat(gpub200::ctx(), s, n, m_nullspace->raw(), n * n, m_projOp->raw(), n * n, nMats));
     /* U and the rank tensor die with `svd` at scope exit: wait for the two launches that read them */
-    Session::getInstance().synchronizeStream(a.streamIdx());
+    Session::getInstance().synchronizeStream(aTranspose.streamIdx());
 }
 
 template<typename T>
@@ -386,6 +391,25 @@ public:
         if (b.numCols() != 1) throw std::invalid_argument("[CholeskyBatchSolve] only supports `b` with one column");
         gpuErrChk(gpub200::Abi<T>::potrs(gpub200::ctx(), (int) m_matrix->streamIdx(), m_numRows, m_matrix->raw(),
                                          m_numRows, m_numRows * m_numRows, b.raw(), m_numRows, m_numMats));
+    }
+
+    /**
+     * Additive API: the whole job from host memory at the speed of the host link. The reference offers whole-tensor calls only
+     * (upload, factorise, solve, download: tensor.cuh:1128-1154, 2135-2197), which serialise three transfers and two kernels;
+     * here the batch is cut into `chunks` pieces that flow through three streams, so the kernels and the download of one piece
+     * hide behind the upload of the next. hostA holds the matrices (numRows^2 values each, column-major, mats slowest), hostB the
+     * right-hand sides; pinned host memory is DMA'd directly, pageable memory is staged. On return the factorised tensor holds
+     * the factors (as after factorise()), `b` and hostX the solutions, info() -- and hostInfo, if given -- the status codes.
+     */
+    void factoriseAndSolveFromHost(const T *hostA, const T *hostB, DTensor<T> &b, T *hostX, int *hostInfo = nullptr,
+                                   size_t chunks = 16) {
+        if (m_factorisationDone) throw std::logic_error("[CholeskyBatch] already factorised");
+        if (m_numRows != b.numRows() || m_numMats != b.numMats() || b.numCols() != 1)
+            throw std::invalid_argument("[CholeskyBatch] A and b incompatible");
+        if (!hostA || !hostB) throw std::invalid_argument("[CholeskyBatch] null host buffer");
+        gpuErrChk(gpub200::Abi<T>::chol_from_host(gpub200::ctx(), (int) m_matrix->streamIdx(), m_numRows, m_matrix->raw(), b.raw(),
+                                                  m_info->raw(), hostA, hostB, hostX, hostInfo, m_numMats, chunks));
+        m_factorisationDone = true;
     }
 };
 

@@ -262,6 +262,14 @@ public:
             send[g] = m_shards[g]->raw();
             recv[g] = full[g]->raw();
             bytes[g] = m_shards[g]->numEl() * sizeof(T);
+            /* the gather runs on stream 0 of every device: work queued on a shard's own stream comes first */
+            if (m_shards[g]->streamIdx() != 0) {
+                cudaEvent_t ev;
+                gpuErrChk(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                gpuErrChk(cudaEventRecord(ev, Session::getInstance().streamOfCurrentDevice(m_shards[g]->streamIdx())));
+                gpuErrChk(cudaStreamWaitEvent(Session::getInstance().streamOfCurrentDevice(0), ev, 0));
+                gpuErrChk(cudaEventDestroy(ev));
+            }
         }
         if (numEl() == 0) return full;
         gpuErrChk(gpub_multi_allgather(ctxs.data(), (int) G, 0, send.data(), bytes.data(), recv.data(), transport, transportUsed));

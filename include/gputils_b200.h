@@ -17,7 +17,8 @@
  *    cuBLAS call it replaces;
  *  - launchers allocate nothing: scratch comes from the caller (`work`,
  *    sized by the matching `*_worksize`) or from the context's per-stream
- *    scratch (reductions only);
+ *    scratch (reductions only); device memory for tensors comes from the
+ *    context's stream-ordered pool (gpub_mem_alloc);
  *  - return value: 0 on success, a positive `cudaError_t` code if the CUDA
  *    runtime failed, a negative GPUB_E* code for argument errors.  Launchers
  *    never throw, print or exit; the C++ header maps non-zero to the
@@ -64,6 +65,29 @@ int gpub_ctx_release(gpub_ctx_t ctx);
 int gpub_ctx_release_all(void);
 int gpub_ctx_device(gpub_ctx_t ctx);
 int gpub_ctx_sm_count(gpub_ctx_t ctx);
+
+/* ---- memory: stream-ordered pool behind Session::cudaAllocate ----------------
+ * ref: tensor.cuh:1106-1126 (two cudaMalloc per DTensor), 283-294 (two cudaFree), and the per-call allocations of tr() (1169),
+ * the binary operators (634, 640) and the Nullspace loop (2076).
+ * gpub_mem_alloc takes `bytes` from the context's pool, ordered on the LEGACY default stream: like cudaMalloc it is an ordering
+ * point for every blocking stream of the context (and for synchronous cudaMemcpy), but it does not stop the host, and freed
+ * blocks stay cached in the pool, so constructing / destroying tensors in a solver loop costs no driver allocation.
+ * gpub_mem_free(ptr) returns a block to the pool it came from (any device may be current). Streams created with
+ * cudaStreamNonBlocking (e.g. adopted with gpub_ctx_bind_stream) are NOT ordered by the legacy stream: order them yourself. */
+int gpub_mem_alloc(gpub_ctx_t ctx, size_t bytes, void **ptr);
+int gpub_mem_free(void *ptr);
+/* bytes the pool holds from the driver / bytes currently handed out */
+int gpub_mem_stats(gpub_ctx_t ctx, size_t *reserved_bytes, size_t *used_bytes);
+/* give cached blocks back to the driver, keeping at most keep_bytes (synchronises the legacy stream) */
+int gpub_mem_trim(gpub_ctx_t ctx, size_t keep_bytes);
+
+/* ---- host <-> device copies ---------------------------------------------------
+ * ref: tensor.cuh:1128-1145 (upload: host-side copy + one pageable cudaMemcpy), 1147-1154 (download).
+ * Blocking like the cudaMemcpy they replace (on return the data has arrived), queued on stream `sidx`. Pinned host memory is
+ * DMA'd directly; pageable memory is cut into 8 MB pieces that several host threads stage through a ring of pinned buffers
+ * while the DMA of the previous piece is in flight. */
+int gpub_upload(gpub_ctx_t ctx, int sidx, void *dst_dev, const void *src_host, size_t bytes);
+int gpub_download(gpub_ctx_t ctx, int sidx, void *dst_host, const void *src_dev, size_t bytes);
 
 /* ---- storage helpers ------------------------------------------------------
  * ref: tensor.cuh:672-688 (pointer table built on the host, then H2D)        */
@@ -137,6 +161,19 @@ int gpub_potrs_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *L, 
                            double *b, size_t strideB, size_t batch);
 int gpub_potrs_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *L, size_t ldl, size_t strideL,
                            float *b, size_t strideB, size_t batch);
+
+/* Host pipeline (additive; the reference has whole-tensor upload -> factorise -> solve -> download, tensor.cuh:1128-1154,
+ * 2135-2197): the dense batch A_host (n*n per matrix) / b_host (n per matrix) is cut into `chunks` pieces (0 = default 16);
+ * each piece is uploaded into A_dev / b_dev, factorised and solved as soon as it has landed, and x / info are downloaded behind
+ * the kernels, on three streams (upload, stream `sidx`, download), so the whole job runs at the host link's speed. On return
+ * (blocking) A_dev holds the factors, b_dev and x_host the solutions, info_dev / info_host the status codes. b_* / x_host /
+ * info_* may be NULL (factorise only / no download). Host buffers may be pinned (DMA'd directly) or pageable (staged). */
+int gpub_chol_solve_from_host_f64(gpub_ctx_t ctx, int sidx, size_t n, double *A_dev, double *b_dev, int *info_dev,
+                                  const double *A_host, const double *b_host, double *x_host, int *info_host,
+                                  size_t batch, size_t chunks);
+int gpub_chol_solve_from_host_f32(gpub_ctx_t ctx, int sidx, size_t n, float *A_dev, float *b_dev, int *info_dev,
+                                  const float *A_host, const float *b_host, float *x_host, int *info_host,
+                                  size_t batch, size_t chunks);
 
 /* ---- batched Householder QR / least squares --------------------------------
  * geqrf: LAPACK storage (R in the upper triangle, reflectors below, tau[n]).

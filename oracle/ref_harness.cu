@@ -12,6 +12,7 @@
 #include <tensor.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 namespace {
@@ -86,6 +87,33 @@ int ref_chol_batch(size_t n, size_t batch, const T *A, T *L, const T *b, T *x, i
     if (ms_factor) *ms_factor = tf.total / std::max(reps, 1);
     if (ms_solve) *ms_solve = ts.total / std::max(reps, 1);
     return 0;
+}
+
+// The reference's host path, as its API prescribes it: upload (tensor.cuh:1128-1145), factorise, solve (2135-2197), download
+// (1147-1154) of whole tensors from / to host vectors. Wall-clock seconds per repetition (the calls block); the tensors are
+// constructed once, outside the timed region.
+template<typename T>
+double ref_chol_batch_host(size_t n, size_t batch, const T *hA, const T *hb, T *hx, int *hinfo, int reps) {
+    std::vector<T> vA(hA, hA + n * n * batch), vb(hb, hb + n * batch), vx;
+    std::vector<int> vi;
+    DTensor<T> dA(n, n, batch), dB(n, 1, batch);
+    double total = 0;
+    for (int r = 0; r < std::max(reps, 1); r++) {
+        gpuErrChk(cudaDeviceSynchronize());
+        auto t0 = std::chrono::steady_clock::now();
+        dA.upload(vA);
+        dB.upload(vb);
+        CholeskyBatchFactoriser<T> chol(dA);
+        chol.factorise();
+        chol.solve(dB);
+        dB.download(vx);
+        chol.info().download(vi);
+        gpuErrChk(cudaDeviceSynchronize());
+        total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (hx) std::copy(vx.begin(), vx.end(), hx);
+    if (hinfo) std::copy(vi.begin(), vi.end(), hinfo);
+    return total / std::max(reps, 1);
 }
 
 template<typename T>
@@ -209,6 +237,9 @@ const char *ref_description(void) { return "GPUtils reference header, cuBLAS/cuS
                         float *ms) { return ref_addAB<T>(m, n, k, batch, A, B, C, alpha, beta, reps, ms); }                \
     int ref_chol_batch_##SUF(size_t n, size_t batch, const T *A, T *L, const T *b, T *x, int *info, int reps, float *msf,  \
                              float *mss) { return ref_chol_batch<T>(n, batch, A, L, b, x, info, reps, msf, mss); }         \
+    double ref_chol_batch_host_##SUF(size_t n, size_t batch, const T *hA, const T *hb, T *hx, int *hinfo, int reps) {       \
+        return ref_chol_batch_host<T>(n, batch, hA, hb, hx, hinfo, reps);                                                  \
+    }                                                                                                                      \
     int ref_gels_##SUF(size_t m, size_t n, size_t batch, const T *A, T *Aout, const T *b, T *bout, int reps, float *ms) {  \
         return ref_gels<T>(m, n, batch, A, Aout, b, bout, reps, ms);                                                       \
     }                                                                                                                      \

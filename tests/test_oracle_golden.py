@@ -133,3 +133,38 @@ def test_generators_are_deterministic(oracle):
     assert a.min() >= -1 and a.max() < 1 and abs(a.mean()) < 0.1
     S = oracle.fill_spd_batched(8, 3, 8.0, 7)
     assert np.all(np.linalg.eigvalsh(S) > 0)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_host_lapack_baseline_agrees_with_the_oracle(oracle, dt):
+    """oracle/cpu_lapack.c (OpenBLAS LAPACK under an OpenMP loop: bench.py's cpu_baseline) computes what the oracle port computes:
+    Cholesky factor + solve, GEMM, least squares, QR and singular values on small seeded batches."""
+    import cpu_lapack as cl
+    tol = 1e-12 if dt == np.float64 else 2e-5
+    k, n = 64, 32
+    A = oracle.fill_spd_batched(n, k, float(n), 5, dt)
+    b = oracle.fill_uniform(k * n, -1.0, 1.0, 6, dt).reshape(k, n, 1)
+    L_o, info_o = oracle.potrf_batched(A)
+    x_o = oracle.potrs_batched(L_o, b)
+    Ac = np.ascontiguousarray(A.transpose(0, 2, 1)); bc = np.ascontiguousarray(b.transpose(0, 2, 1)); info = np.ones(k, np.int32)
+    assert cl.chol_batch(Ac, bc, info, threads=2) > 0 and not info.any()
+    assert np.linalg.norm(np.tril(Ac.transpose(0, 2, 1)) - np.tril(L_o)) <= tol * np.linalg.norm(L_o)
+    assert np.linalg.norm(bc.transpose(0, 2, 1) - x_o) <= 50 * tol * np.linalg.norm(x_o)
+    B = oracle.fill_uniform(k * n * n, -1.0, 1.0, 7, dt).reshape(k, n, n)
+    Cc = np.zeros((k, n, n), dt)
+    assert cl.gemm_batch(np.ascontiguousarray(A.transpose(0, 2, 1)), np.ascontiguousarray(B.transpose(0, 2, 1)), Cc) > 0
+    ref = oracle.gemm_batched(A, B)
+    assert np.linalg.norm(Cc.transpose(0, 2, 1) - ref) <= tol * np.linalg.norm(ref)
+    m, nn = 64, 16
+    T = oracle.fill_uniform(k * m * nn, -1.0, 1.0, 8, dt).reshape(k, m, nn); r = oracle.fill_uniform(k * m, -1.0, 1.0, 9, dt).reshape(k, m, 1)
+    _, xb_o, _ = oracle.gels_batched(T, r)
+    Tc = np.ascontiguousarray(T.transpose(0, 2, 1)); rc = np.ascontiguousarray(r.transpose(0, 2, 1))
+    assert cl.gels_batch(Tc, rc) > 0
+    assert np.linalg.norm(rc[:, 0, :nn] - xb_o[:, :nn, 0]) <= 100 * tol * np.linalg.norm(xb_o[:, :nn])
+    Tc = np.ascontiguousarray(T.transpose(0, 2, 1)); tau = np.zeros((k, nn), dt)
+    assert cl.geqrf_batch(Tc, tau) > 0
+    qr_o, tau_o = oracle.geqrf_batched(T)
+    assert np.linalg.norm(Tc.transpose(0, 2, 1) - qr_o) <= 100 * tol * np.linalg.norm(qr_o) and np.linalg.norm(tau - tau_o) <= 100 * tol * np.linalg.norm(tau_o)
+    Tc = np.ascontiguousarray(T.transpose(0, 2, 1)); S = np.zeros((k, nn), dt); Vt = np.zeros((k, nn, nn), dt)
+    assert cl.gesvd_batch(Tc, S, None, Vt) > 0
+    assert np.linalg.norm(S - np.linalg.svd(T.astype(np.float64), compute_uv=False)) <= 100 * tol * np.linalg.norm(S)
