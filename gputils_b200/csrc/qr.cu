@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(QT) k_geqrf_wy(int m, int n, T *A, size_t lda,
 // Output is LAPACK's (R on / above the diagonal, reflectors below, tau), same dlarfg rule as the other kernels.
 // ------------------------------------------------------------------------------------------
 #ifdef GPUB_TCQ_PROFILE
-__device__ unsigned long long g_tcq_prof[8];
+__device__ unsigned long long g_tcq_prof[12];
 #define TCQ_T(idx) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_tcq_prof[idx], (unsigned long long) (t_ - tcq_t0)); tcq_t0 = t_; } } while (0)
 #else
 #define TCQ_T(idx) do { } while (0)
@@ -518,42 +518,14 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
     if constexpr (JJ + 1 < TCQ_NB) tcq_panel_column<RPT, JJ + 1>(p, rr, sh, warp, lane, tau_g, tau_ok_upto);
 }
 
-// G = V^T V, T, and the trailing update A2 <- (I - V T^T V^T) A2 for one panel
-// tgt: matrix whose columns [col0, col_end) are updated on rows j0 .. j0 + mj - 1 (leading dimension ldt). TRT: apply
-// I - V T^T V^T (Q^T, what geqrf needs) when true, I - V T V^T (Q) when false.
-template<bool TRT>
-__device__ __forceinline__ void tcq_trailing(TcqShared sh, double *tgt, size_t ldt, int col0, int col_end, int j0, int mj, int ldv
-#ifdef GPUB_TCQ_PROFILE
-                                          , long long &tcq_t0
-#endif
-) {
+// Gs (upper triangle with diagonal) = X^T X of the 16 columns stored in the V buffer ([column][row], zero beyond the last row):
+// DMMA tiles over 16 row ranges (one per warp; lane (g, q) takes rows r + 2q, r + 2q + 1 of a chunk of 8: one LDS.128 per fragment
+// pair, the k order inside a chunk is free), per-warp partials through shared memory, fixed summation order
+__device__ __forceinline__ void tcq_gram(const TcqShared &sh, int mj16, int ldv) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int mj16 = (mj + 15) & ~15;
-    const int ntrail = col_end - col0;
     const unsigned vs_sh = (unsigned) __cvta_generic_to_shared(sh.Vs());
-    const unsigned v8off = (unsigned) (8 * ldv * 8);   // byte offset of V column c + 8
-    const int ncb = (ntrail + 7) / 8;
-    const int rg = warp >> 2, cq = warp & 3;
-    const int rpg = (((mj16 >> 2) + 7) & ~7);          // pass 1: rows per row group, multiple of 8
-    // L2 prefetch of this warp's pass-1 operand (its rows of its column blocks) for the chunk starting at cbs:
-    // issued a whole phase ahead, so pass 1 streams from L2 instead of waiting on DRAM. lane -> (column, 128-byte line)
-    auto prefetch_chunk = [&](int cbs) {
-        const int r0 = rg * rpg;
-#pragma unroll
-        for (int sl = 0; sl < TCQ_NSL; sl++) {
-            const int cb = cbs + cq + 4 * sl, col = col0 + 8 * cb + (lane & 7);
-            if (cb < ncb && col < col_end) {
-                const double *base = tgt + (size_t) j0 + (size_t) col * ldt + r0;
-                for (int ln = lane >> 3; 16 * ln < rpg && r0 + 16 * ln < mj; ln += 4)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 16 * ln));
-            }
-        }
-    };
-    const int cb_last = ((ncb - 1) / (4 * TCQ_NSL)) * (4 * TCQ_NSL);
-    prefetch_chunk(cb_last);
-    // ---- G = V^T V: each warp one row range, upper three 8 x 8 tiles. Lane (g, q) takes rows r + 2q, r + 2q + 1
-    //      of a chunk of 8 (one LDS.128 per fragment pair; the k order inside a chunk is free) ----
+    const unsigned v8off = (unsigned) (8 * ldv * 8);   // byte offset of column c + 8
     {
         const int kr = ((mj16 / 8 + TCQ_WARPS - 1) / TCQ_WARPS) * 8;
         const int r0 = warp * kr, r1 = (r0 + kr) < mj16 ? (r0 + kr) : mj16;
@@ -573,7 +545,7 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *tgt, size_t l
     __syncthreads();
     if (tid < 256) {
         const int i = tid >> 4, j = tid & 15;
-        if (i < j && !(i >= 8 && j < 8)) {
+        if (i <= j) {
             double acc = 0.0;
 #pragma unroll
             for (int w = 0; w < TCQ_WARPS; w++) acc += sh.part()[(size_t) w * 256 + tid];
@@ -581,6 +553,12 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *tgt, size_t l
         }
     }
     __syncthreads();
+}
+
+// T of the compact WY form from G = V^T V (strict upper triangle) and tau: T(i, j) = -tau_j sum_k T(i, k) G(k, j), one lane per row
+__device__ __forceinline__ void tcq_form_T(const TcqShared &sh, int mj16, int ldv) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    tcq_gram(sh, mj16, ldv);
     if (warp == 0 && lane < TCQ_NB) {
         double trow[TCQ_NB];
 #pragma unroll
@@ -595,195 +573,339 @@ __device__ __forceinline__ void tcq_trailing(TcqShared sh, double *tgt, size_t l
         }
     }
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-split trailing update: tgt <- (I - V T' V') tgt (TRT; I - V T V' otherwise) with every column read ONCE and written ONCE.
+// tgt: matrix whose columns [col0, col_end) are updated on rows j0 .. j0 + mj - 1 (leading dimension ldt).
+// The 16 warps split the ROWS (8-row groups, GPW per warp); for a pair of 8-column blocks a lane keeps its piece of the columns in
+// registers across both passes: lane (g, q) holds rows 8t + 2q, 8t + 2q + 1 of column g of every group t of its warp -- that is
+// the B fragment of pass 1 (W = V' A2: the k order inside a group is free, k-slot q takes row 2q, then row 2q + 1) AND the
+// accumulator of pass 2 computed transposed (D'(column, row) += W'' V'), so no layout change and no second trip to memory.
+// Per pair of column blocks: partial W of the 16 warps -> shared memory -> summed -> W' = -T' W -> pass 2, three CTA barriers.
+// (Measured and rejected: two independent halves of 8 warps on alternating column blocks, named barriers -- 1.05 instead of
+// 0.92 ms: the update is bound by the bytes it moves through L2, not by exposed latency.)
+// ncu of the column-split predecessor (one warp per 8 columns, the column streamed from L2 in each pass): DRAM 2.67 x the
+// algorithmic bytes and an FP64 pipe 10 % busy behind global-memory fragment loads.
+// ------------------------------------------------------------------------------------------
+template<bool TRT, int GPW>
+__device__ __forceinline__ void tcq_trailing_rs(TcqShared sh, double *tgt, size_t ldt, int col0, int col_end, int j0, int mj, int ldv
+#ifdef GPUB_TCQ_PROFILE
+                                                , long long &tcq_t0
+#endif
+) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int mj16 = (mj + 15) & ~15;
+    const int ncb = (col_end - col0 + 7) / 8;
+    const unsigned vs_sh = (unsigned) __cvta_generic_to_shared(sh.Vs());
+    const unsigned v8off = (unsigned) (8 * ldv * 8);
+    const unsigned s4off = (unsigned) (4 * ldv * 8);
+    tcq_form_T(sh, mj16, ldv);
     TCQ_T(3);
-    // ---- trailing update: the 16 warps form a 4 (row groups) x 4 (column groups) grid; chunks of 16 column blocks ----
-    // A slot whose column block does not exist (or a lane whose column is >= n) reads a valid dummy column instead
-    // and never stores: the hot loops carry no load predicates. Every global access is 128-bit: the order of k inside
-    // a DMMA chunk and the assignment of tile rows are free, so lane (g, q) takes the row PAIRS r + 2q, r + 2q + 1
-    // (pass 1) and r + 2g, r + 2g + 1 (pass 2); a fragment load then moves 64 B (pass 1) or 128 B (pass 2) per
-    // cache line instead of 32 B, which is what keeps the L1 wavefront rate below the DMMA issue rate.
-    // chunks of 4 * TCQ_NSL column blocks, last chunk first: a chunk's pass 2 re-reads what its pass 1 just read while it is
-    // still in L2, and the columns of the next panel (chunk 0) are the most recently written when they are reloaded
-    for (int cb0 = cb_last; cb0 >= 0; cb0 -= 4 * TCQ_NSL) {
-        // pass 1: partial W = V^T A2 over the rows of this row group, for the (up to 4) column blocks cq, cq+4, ...
+    // this warp's 8-row groups [t0, t1)
+    const int ng = mj16 >> 3;
+    const int gpw = (ng + TCQ_WARPS - 1) / TCQ_WARPS;
+    const int t0 = warp * gpw;
+    const int t1 = (t0 + gpw) < ng ? (t0 + gpw) : ng;
+    double *wsum = sh.wp() + 1024;                          // [2 slots][16 panel columns][8 columns]
+    for (int cb0 = 0; cb0 < ncb; cb0 += 2) {
+        double2 a[2][GPW];
+        double *cp[2];
+        unsigned okmask = 0;
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            const int cb = cb0 + sl, c0 = col0 + 8 * cb;
+            const bool ok = cb < ncb && c0 + g < col_end;   // a lane beyond the last column reads a valid one and never stores
+            okmask |= (ok ? 1u : 0u) << sl;
+            cp[sl] = tgt + (size_t) j0 + (size_t) (ok ? c0 + g : col0) * ldt + 2 * q;
+#pragma unroll
+            for (int i = 0; i < GPW; i++) {
+                const int r = 8 * (t0 + i) + 2 * q;
+                if (t0 + i < t1 && r + 1 < mj) a[sl][i] = *reinterpret_cast<const double2 *>(cp[sl] + 8 * (t0 + i));
+                else {
+                    a[sl][i].x = (t0 + i < t1 && r < mj) ? cp[sl][8 * (t0 + i)] : 0.0;
+                    a[sl][i].y = 0.0;
+                }
+            }
+        }
+        // L2 prefetch of this warp's rows of the next pair of column blocks: one lane per 128-byte line (16 rows of a column)
+        if (cb0 + 2 < ncb && q == 0) {
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int c = col0 + 8 * (cb0 + 2 + sl) + g;
+                if (c < col_end) {
+                    const double *nx = tgt + (size_t) j0 + (size_t) c * ldt;
+#pragma unroll
+                    for (int i = 0; i < GPW; i += 2)
+                        if (t0 + i < t1 && 8 * (t0 + i) < mj) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 8 * (t0 + i)));
+                }
+            }
+        }
+#ifdef GPUB_TCQ_PROFILE
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++)
+#pragma unroll
+            for (int i = 0; i < GPW; i++) asm volatile("" ::"d"(a[sl][i].x), "d"(a[sl][i].y));
+        TCQ_T(7);
+#endif
+        // ---- pass 1: partial W (16 panel columns x 8 columns per slot) over this warp's rows ----
         {
-            const int r0 = rg * rpg;
-            const int r1 = (r0 + rpg) < mj16 ? (r0 + rpg) : mj16;
-            const double *a2[TCQ_NSL];
+            double acc[2][2][2];
 #pragma unroll
-            for (int sl = 0; sl < TCQ_NSL; sl++) {
-                const int cb = cb0 + cq + 4 * sl, c0 = col0 + 8 * cb;
-                const bool ok = cb < ncb && c0 + g < col_end;
-                a2[sl] = tgt + (size_t) j0 + (size_t) (ok ? c0 + g : col0) * ldt + 2 * q + r0;
-            }
-            double acc[TCQ_NSL][2][2];
+            for (int sl = 0; sl < 2; sl++) acc[sl][0][0] = acc[sl][0][1] = acc[sl][1][0] = acc[sl][1][1] = 0.0;
+            const unsigned va = vs_sh + (unsigned) ((g * ldv + 2 * q + 8 * t0) * 8);
 #pragma unroll
-            for (int sl = 0; sl < TCQ_NSL; sl++) acc[sl][0][0] = acc[sl][0][1] = acc[sl][1][0] = acc[sl][1][1] = 0.0;
-            unsigned v0a = vs_sh + (unsigned) ((g * ldv + 2 * q + r0) * 8);
-            const int rlim = r1 < mj ? r1 : mj;
-            const int nfull = rlim > r0 ? (rlim - r0) >> 3 : 0;     // chunks of 8 rows that need no row guard
-            // software pipeline over chunks of 8 rows, TCQ_D1 - 1 chunks of loads in flight per warp (the pass is bound by
-            // bytes in flight x memory latency, not by the DMMA pipe, unless the prefetch distance is this deep)
-            double2 bq[TCQ_D1][TCQ_NSL];
-            auto ld = [&](double2 (&bb)[TCQ_NSL], int off_) {
+            for (int i = 0; i < GPW; i++) {
+                if (t0 + i < t1) {
+                    const double2 f0 = lds_f64x2(va + 64 * i), f1 = lds_f64x2(va + 64 * i + v8off);
 #pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) bb[sl] = *reinterpret_cast<const double2 *>(a2[sl] + off_);
-            };
-            auto mm = [&](const double2 (&bb)[TCQ_NSL], unsigned va_) {
-                const double2 f0 = lds_f64x2(va_), f1 = lds_f64x2(va_ + v8off);
+                    for (int sl = 0; sl < 2; sl++) {
+                        dmma884(acc[sl][0][0], acc[sl][0][1], f0.x, a[sl][i].x);
+                        dmma884(acc[sl][1][0], acc[sl][1][1], f1.x, a[sl][i].x);
+                    }
 #pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    dmma884(acc[sl][0][0], acc[sl][0][1], f0.x, bb[sl].x);
-                    dmma884(acc[sl][1][0], acc[sl][1][1], f1.x, bb[sl].x);
-                }
-#pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    dmma884(acc[sl][0][0], acc[sl][0][1], f0.y, bb[sl].y);
-                    dmma884(acc[sl][1][0], acc[sl][1][1], f1.y, bb[sl].y);
-                }
-            };
-#pragma unroll
-            for (int d = 0; d < TCQ_D1 - 1; d++)
-                if (d < nfull) ld(bq[d], 8 * d);
-            int ch = 0;
-            for (; ch + TCQ_D1 <= nfull; ch += TCQ_D1) {
-#pragma unroll
-                for (int d = 0; d < TCQ_D1; d++) {
-                    if (ch + d + TCQ_D1 - 1 < nfull) ld(bq[(d + TCQ_D1 - 1) % TCQ_D1], 8 * (ch + d + TCQ_D1 - 1));
-                    mm(bq[d], v0a + 64 * (ch + d));
+                    for (int sl = 0; sl < 2; sl++) {
+                        dmma884(acc[sl][0][0], acc[sl][0][1], f0.y, a[sl][i].y);
+                        dmma884(acc[sl][1][0], acc[sl][1][1], f1.y, a[sl][i].y);
+                    }
                 }
             }
+            // part[warp][slot][panel column k][column c]: lane (g, q) holds W(8 mt + g, 2q), W(8 mt + g, 2q + 1)
 #pragma unroll
-            for (int d = 0; d < TCQ_D1 - 1; d++)
-                if (ch + d < nfull) mm(bq[d], v0a + 64 * (ch + d));
-            int off = 8 * nfull;
-            v0a += 64 * nfull;
-            for (int r = r0 + off; r < r1; r += 8, off += 8, v0a += 64) {   // guarded tail (V is zero beyond mj)
-                double2 bt[TCQ_NSL];
+            for (int sl = 0; sl < 2; sl++)
 #pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    bt[sl].x = (r + 2 * q < mj) ? a2[sl][off] : 0.0;
-                    bt[sl].y = (r + 2 * q + 1 < mj) ? a2[sl][off + 1] : 0.0;
-                }
-                mm(bt, v0a);
-            }
-            // partial W of (row group, column block) -> part[rg][cbl][column][k]
-#pragma unroll
-            for (int sl = 0; sl < TCQ_NSL; sl++) {
-                double *pw = sh.part() + (size_t) (rg * 16 + cq + 4 * sl) * 128;
-#pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    pw[(2 * q) * 16 + 8 * a + g] = acc[sl][a][0];
-                    pw[(2 * q + 1) * 16 + 8 * a + g] = acc[sl][a][1];
-                }
-            }
+                for (int mt = 0; mt < 2; mt++)
+                    *reinterpret_cast<double2 *>(sh.part() + (size_t) ((warp * 2 + sl) * 16 + 8 * mt + g) * 8 + 2 * q) =
+                        make_double2(acc[sl][mt][0], acc[sl][mt][1]);
         }
         __syncthreads();
         TCQ_T(4);
-        // W' = -T^T W for column block cbl = warp of this chunk: lane -> column c = lane & 7, rows i = (lane >> 3) + 4u
-        if (warp < 4 * TCQ_NSL && cb0 + warp < ncb) {
-            const int c = lane & 7;
-            double wc[TCQ_NB];
-            // (the 8 columns are 16 doubles apart: reading k in the rotated order (kk + 2c) & 15 spreads them over the banks)
+        if (tid < 256) {
+            const int sl = tid >> 7, e = tid & 127;
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < TCQ_NB; kk++) {
-                const double *pp = sh.part() + (size_t) warp * 128 + c * 16 + ((kk + 2 * c) & 15);
-                wc[kk] = (pp[0] + pp[16 * 128]) + (pp[32 * 128] + pp[48 * 128]);
+            for (int w = 0; w < TCQ_WARPS; w += 2) {
+                s0 += sh.part()[(size_t) ((w * 2 + sl) * 128) + e];
+                s1 += sh.part()[(size_t) (((w + 1) * 2 + sl) * 128) + e];
             }
+            wsum[tid] = s0 + s1;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            // W'(i, c) = -sum_k T(k, i) W(k, c) (T' for geqrf / Q'), -sum_k T(i, k) W(k, c) for Q
+            const int sl = tid >> 7, i = (tid >> 3) & 15, c = tid & 7;
+            double acc = 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = (lane >> 3) + 4 * u;
-                double acc = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < TCQ_NB; kk++) {
-                    const int k = (kk + 2 * c) & 15;
-                    const double t = TRT ? (k <= i ? sh.Ts()[k * 17 + i] : 0.0) : (k >= i ? sh.Ts()[i * 17 + k] : 0.0);
-                    acc = fma(t, wc[kk], acc);
-                }
-                sh.wp()[(size_t) warp * (8 * TCQ_LDW) + c * TCQ_LDW + i] = -acc;
+            for (int k = 0; k < TCQ_NB; k++) {
+                const double t = TRT ? (k <= i ? sh.Ts()[k * 17 + i] : 0.0) : (k >= i ? sh.Ts()[i * 17 + k] : 0.0);
+                acc = fma(t, wsum[sl * 128 + k * 8 + c], acc);
             }
+            sh.wp()[(size_t) (sl * 8 + c) * TCQ_LDW + i] = -acc;
         }
         __syncthreads();
         TCQ_T(5);
-        // pass 2: A2 blocks of 16 rows x 8 columns of this row group += V W', computed TRANSPOSED: D'(column, row) += W'^T V^T,
-        // so that lane (g, q) holds rows 2q, 2q + 1 of column g (one 128-bit access per tile; a quarter-warp touches two
-        // cache lines instead of four). A operand = W'^T (the same registers bw), B operand = V^T from shared memory.
-        if (cb0 > 0) prefetch_chunk(cb0 - 4 * TCQ_NSL);
+        // ---- pass 2: D'(column g, rows 2q, 2q + 1) += sum_k W'(k, column) V(row, k): A = W'', B = V' from shared memory ----
         {
-            const int nblk = mj16 >> 4;
-            const int bpg = (nblk + 3) >> 2;
-            const int b0 = rg * bpg;
-            const int b1 = (b0 + bpg) < nblk ? (b0 + bpg) : nblk;
-            double bw[TCQ_NSL][4];
-            double *cp[TCQ_NSL];      // rows 2q, 2q + 1 of column g of the slot's block
-            unsigned okmask = 0;      // bit sl: this lane's column of slot sl exists and is stored
+            double bw[2][4];
 #pragma unroll
-            for (int sl = 0; sl < TCQ_NSL; sl++) {
-                const int cbl = cq + 4 * sl, cb = cb0 + cbl, c0 = col0 + 8 * cb;
-                const bool live = cb < ncb;
-                const bool ok = live && c0 + g < col_end;
-                okmask |= (ok ? 1u : 0u) << sl;
+            for (int sl = 0; sl < 2; sl++)
 #pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) bw[sl][s4] = live ? sh.wp()[(size_t) cbl * (8 * TCQ_LDW) + g * TCQ_LDW + 4 * s4 + q] : 0.0;
-                cp[sl] = tgt + (size_t) j0 + (size_t) (ok ? c0 + g : col0) * ldt + 2 * q + 16 * b0;
-            }
-            unsigned vaa = vs_sh + (unsigned) ((q * ldv + g + 16 * b0) * 8);
-            const unsigned s4off = (unsigned) (4 * ldv * 8);
-            const int bfull = (mj >> 4) < b1 ? (mj >> 4) : b1;       // blocks [b0, bfull) need no row guard
-            int off = 0, rb = b0;
-            for (; rb < bfull; rb++, off += 16, vaa += 128) {
-                double2 t1[TCQ_NSL], t2[TCQ_NSL];
+                for (int s4 = 0; s4 < 4; s4++) bw[sl][s4] = sh.wp()[(size_t) (sl * 8 + g) * TCQ_LDW + 4 * s4 + q];
+            const unsigned vb = vs_sh + (unsigned) ((q * ldv + g + 8 * t0) * 8);
 #pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    t1[sl] = *reinterpret_cast<const double2 *>(cp[sl] + off);
-                    t2[sl] = *reinterpret_cast<const double2 *>(cp[sl] + off + 8);
-                }
+            for (int i = 0; i < GPW; i++) {
+                if (t0 + i < t1) {
 #pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) {
-                    const double vb1 = lds_f64(vaa + s4 * s4off), vb2 = lds_f64(vaa + s4 * s4off + 64);
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const double v = lds_f64(vb + 64 * i + s4 * s4off);
 #pragma unroll
-                    for (int sl = 0; sl < TCQ_NSL; sl++) {
-                        dmma884(t1[sl].x, t1[sl].y, bw[sl][s4], vb1);
-                        dmma884(t2[sl].x, t2[sl].y, bw[sl][s4], vb2);
-                    }
-                }
-#pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    if (okmask & (1u << sl)) {
-                        *reinterpret_cast<double2 *>(cp[sl] + off) = t1[sl];
-                        *reinterpret_cast<double2 *>(cp[sl] + off + 8) = t2[sl];
-                    }
-                }
-            }
-            for (; rb < b1; rb++, off += 16, vaa += 128) {           // the partial last block (V is zero beyond mj)
-                const int rbase = 16 * rb + 2 * q;
-                double2 t1[TCQ_NSL], t2[TCQ_NSL];
-#pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    t1[sl].x = rbase < mj ? cp[sl][off] : 0.0;          t1[sl].y = rbase + 1 < mj ? cp[sl][off + 1] : 0.0;
-                    t2[sl].x = rbase + 8 < mj ? cp[sl][off + 8] : 0.0;  t2[sl].y = rbase + 9 < mj ? cp[sl][off + 9] : 0.0;
-                }
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) {
-                    const double vb1 = lds_f64(vaa + s4 * s4off), vb2 = lds_f64(vaa + s4 * s4off + 64);
-#pragma unroll
-                    for (int sl = 0; sl < TCQ_NSL; sl++) {
-                        dmma884(t1[sl].x, t1[sl].y, bw[sl][s4], vb1);
-                        dmma884(t2[sl].x, t2[sl].y, bw[sl][s4], vb2);
-                    }
-                }
-#pragma unroll
-                for (int sl = 0; sl < TCQ_NSL; sl++) {
-                    if (okmask & (1u << sl)) {
-                        if (rbase < mj) cp[sl][off] = t1[sl].x;
-                        if (rbase + 1 < mj) cp[sl][off + 1] = t1[sl].y;
-                        if (rbase + 8 < mj) cp[sl][off + 8] = t2[sl].x;
-                        if (rbase + 9 < mj) cp[sl][off + 9] = t2[sl].y;
+                        for (int sl = 0; sl < 2; sl++) dmma884(a[sl][i].x, a[sl][i].y, bw[sl][s4], v);
                     }
                 }
             }
         }
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            if (okmask & (1u << sl)) {
+#pragma unroll
+                for (int i = 0; i < GPW; i++) {
+                    const int r = 8 * (t0 + i) + 2 * q;
+                    if (t0 + i < t1) {
+                        if (r + 1 < mj) *reinterpret_cast<double2 *>(cp[sl] + 8 * (t0 + i)) = a[sl][i];
+                        else if (r < mj) cp[sl][8 * (t0 + i)] = a[sl][i].x;
+                    }
+                }
+            }
+        }
+        TCQ_T(6);
     }
+}
+
+// dlarfg from alpha and the squared norm of the entries below it, without the sqrt / divide slow paths (as tcq_panel_column)
+__device__ __forceinline__ void tcq_larfg(double alpha, double xnorm2, double &beta, double &tau, double &scale) {
+    tau = 0.0; scale = 0.0; beta = alpha;
+    if (xnorm2 != 0.0) {
+        const double ss = fma(alpha, alpha, xnorm2);
+        double rn;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(ss));
+        const double hs = 0.5 * ss;
+        rn = fma(rn, fma(-hs, rn * rn, 0.5), rn);
+        rn = fma(rn, fma(-hs, rn * rn, 0.5), rn);
+        double nrm = ss * rn;
+        nrm = fma(fma(-nrm, nrm, ss), 0.5 * rn, nrm);
+        beta = alpha >= 0.0 ? -nrm : nrm;
+        const double rbeta = alpha >= 0.0 ? -rn : rn;
+        const double num = beta - alpha;
+        tau = num * rbeta;
+        tau = fma(fma(-tau, beta, num), rbeta, tau);
+        const double den = alpha - beta;
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+        y = fma(fma(-den, y, 1.0), y, y);
+        y = fma(fma(-den, y, 1.0), y, y);
+        scale = fma(fma(-den, y, 1.0), y, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gram panel (GPUB_TCQ_GRAMPANEL): the 16 Householder steps of a panel without a CTA barrier per column.
+// A reflection is orthogonal on the rows it touches, so the Gram matrix S of the ACTIVE rows (>= j) of the panel only loses the
+// pivot row from step to step: S(j+1) = S(j) - R(j, :)' R(j, :) -- the Cholesky recurrence of G = P'P. Everything a step needs
+// from the 1024 rows is in S: |x|^2 = S(j, j) - alpha^2 and x'a_c = S(j, c) - alpha P(j, c), where alpha and P(j, c) belong to
+// the pivot row. So ONE warp runs all 16 steps on G (one DMMA pass over the panel) and the top 16 x 16 block (lane = column),
+// and publishes per step the scale 1 / (alpha - beta) and the update coefficients tau v'a_c; every other row then replays the 16
+// rank-1 updates thread-locally. Two CTA barriers per panel instead of 16.
+// The recurrence is as accurate as the panel is well conditioned (errors grow like eps cond^2): a step whose remaining column
+// norm S(j, j) has dropped below 1e-3 of the column's own norm, or whose |x|^2 is below 1e-6 of it (a column that is already
+// reduced, where LAPACK would return tau = 0), flags the panel and the whole panel is redone by the column-by-column path.
+// ------------------------------------------------------------------------------------------
+#ifndef GPUB_TCQ_GRAMPANEL
+#define GPUB_TCQ_GRAMPANEL 1
+#endif
+constexpr int TCQ_OFF_TW = TCQ_OFF_WP;                  // [16][16] tau_j v_j'a_c (the W' scratch is free during the panel)
+constexpr int TCQ_OFF_SC = TCQ_OFF_WP + 256;            // [16] scale_j
+constexpr int TCQ_OFF_TB = TCQ_OFF_WP + 272;            // [16][16] factored top block (R on / above, V below the diagonal)
+constexpr int TCQ_OFF_FLAG = TCQ_OFF_WP + 528;          // panel must be redone column by column
+
+template<int J>
+__device__ __forceinline__ void tcq_gram_step(double (&b)[TCQ_NB], double (&s)[TCQ_NB], double gd, int c, int nb, const TcqShared &sh,
+                                              double *tau_g, int &bad) {
+    // no branch on nb: the 16 steps are one straight line of code, so the updates of step J that the next pivot does not need
+    // overlap the latency chain (rsqrt, rcp, Newton steps) of step J + 1. Columns beyond nb are zero: tau = 0, nothing changes.
+    const double alpha = __shfl_sync(0xffffffffu, b[J], J);
+    const double sjj = __shfl_sync(0xffffffffu, s[J], J);
+    const double gjj = __shfl_sync(0xffffffffu, gd, J);
+    const double xnorm2 = fma(-alpha, alpha, sjj);
+    if (J < nb && (!(sjj > 1e-3 * gjj) || !(xnorm2 > 1e-6 * sjj))) bad = 1;
+    double beta, tau, scale;
+    tcq_larfg(alpha, xnorm2 > 0.0 ? xnorm2 : 0.0, beta, tau, scale);
+    const double pjc = b[J];
+    const double dot = fma(-alpha, pjc, s[J]);          // x'a_c over the rows below the pivot
+    const double tw = tau * fma(scale, dot, pjc);       // tau v'a_c
+    const double rjc = c > J ? pjc - tw : (c == J ? beta : 0.0);
+    if (c > J && c < TCQ_NB) sh.base[TCQ_OFF_TW + J * 16 + c] = tw;
+    if (c == J) {
+        sh.base[TCQ_OFF_SC + J] = scale;
+        sh.taus()[J] = tau;
+        if (J < nb) tau_g[J] = tau;
+    }
+#pragma unroll
+    for (int r = J + 1; r < TCQ_NB; r++) {
+        const double vr = scale * __shfl_sync(0xffffffffu, b[r], J);
+        b[r] = c > J ? fma(-tw, vr, b[r]) : (c == J ? vr : b[r]);
+    }
+    if (c >= J) b[J] = rjc;
+#pragma unroll
+    for (int a = J + 1; a < TCQ_NB; a++) {
+        const double ra = __shfl_sync(0xffffffffu, rjc, a);
+        if (c >= a) s[a] = fma(-ra, rjc, s[a]);
+    }
+    if constexpr (J + 1 < TCQ_NB) tcq_gram_step<J + 1>(b, s, gd, c, nb, sh, tau_g, bad);
+}
+
+// returns true when the panel was factored (p holds R / V, taus are published); false: p is untouched, use the column path
+template<int RPT>
+__device__ __forceinline__ bool tcq_gram_panel(double (&p)[TCQ_NB][RPT], const int (&rr)[RPT], const TcqShared &sh, int mj16, int nb, int ldv,
+                                               double *tau_g
+#ifdef GPUB_TCQ_PROFILE
+                                               , long long &tcq_t0
+#endif
+) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the raw panel into the V buffer ([column][row], zero padded), then G = P'P on the tensor pipe
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        const int r = tid + TCQ_THREADS * i;
+        if (r < mj16) {
+#pragma unroll
+            for (int c = 0; c < TCQ_NB; c++) sh.Vs()[(size_t) c * ldv + r] = p[c][i];
+        }
+    }
+    __syncthreads();
+    tcq_gram(sh, mj16, ldv);
+    TCQ_T(8);
+    if (warp == 0) {
+        const int c = lane & 15;
+        double b[TCQ_NB], s[TCQ_NB];
+#pragma unroll
+        for (int r = 0; r < TCQ_NB; r++) {
+            b[r] = sh.Vs()[(size_t) c * ldv + r];
+            s[r] = r <= c ? sh.Gs()[r * 17 + c] : 0.0;
+        }
+        double gd = 0.0;
+#pragma unroll
+        for (int r = 0; r < TCQ_NB; r++) gd = r == c ? s[r] : gd;
+        int bad = 0;
+        tcq_gram_step<0>(b, s, gd, lane < 16 ? c : 99, nb, sh, tau_g, bad);
+        if (lane < 16) {
+#pragma unroll
+            for (int r = 0; r < TCQ_NB; r++) sh.base[TCQ_OFF_TB + r * 16 + c] = b[r];
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) reinterpret_cast<int *>(sh.base + TCQ_OFF_FLAG)[0] = bad;
+    }
+    __syncthreads();
+    TCQ_T(9);
+    // the panel comes back from the V buffer: its registers are free while warp 0 runs the recurrence (no spills there)
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        const int r = tid + TCQ_THREADS * i;
+#pragma unroll
+        for (int c = 0; c < TCQ_NB; c++) p[c][i] = r < mj16 ? sh.Vs()[(size_t) c * ldv + r] : 0.0;
+    }
+    if (reinterpret_cast<const int *>(sh.base + TCQ_OFF_FLAG)[0]) {
+        __syncthreads();                                    // everyone has its rows before the column path reuses the scratch
+        return false;
+    }
+    // rows below the top block replay the 16 rank-1 updates (the coefficient row of a step is read when the step starts: the
+    // compiler barrier keeps the 136 coefficients from being hoisted into registers all at once)
+#pragma unroll
+    for (int j = 0; j < TCQ_NB; j++) {
+        asm volatile("" ::: "memory");
+        const double sc = sh.base[TCQ_OFF_SC + j];
+        double vj[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; i++) vj[i] = sc * p[j][i];
+#pragma unroll
+        for (int c = j + 1; c < TCQ_NB; c++) {
+            const double tw = sh.base[TCQ_OFF_TW + j * 16 + c];
+#pragma unroll
+            for (int i = 0; i < RPT; i++) p[c][i] = fma(-tw, vj[i], p[c][i]);
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; i++) p[j][i] = vj[i];
+    }
+    // the rows of the top block come from the recurrence itself
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        if (rr[i] >= 0 && rr[i] < TCQ_NB) {
+#pragma unroll
+            for (int c = 0; c < TCQ_NB; c++) p[c][i] = sh.base[TCQ_OFF_TB + rr[i] * 16 + c];
+        }
+    }
+    TCQ_T(10);
+    return true;
 }
 
 template<int RPT>
@@ -818,7 +940,14 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
                 if (!ok) rr[i] = -1;                     // never "below the pivot"
             }
             TCQ_T(0);
-            tcq_panel_column<RPT, 0>(p, rr, sh, warp, lane, tau_g + j0, nb);
+#if GPUB_TCQ_GRAMPANEL
+            if (!tcq_gram_panel<RPT>(p, rr, sh, mj16, nb, ldv, tau_g + j0
+#ifdef GPUB_TCQ_PROFILE
+                                     , tcq_t0
+#endif
+                                     ))
+#endif
+                tcq_panel_column<RPT, 0>(p, rr, sh, warp, lane, tau_g + j0, nb);
             TCQ_T(1);
             // ---- factored panel back to global memory; explicit V (unit diagonal, zeros above) to shared memory ----
 #pragma unroll
@@ -836,9 +965,9 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_geqrf_tc(int m, int n, doubl
             if (ntrail <= 0) { __syncthreads(); continue; }
             __syncthreads();
             TCQ_T(2);
-            tcq_trailing<true>(sh, a_g, lda, j0 + TCQ_NB, n, j0, mj, ldv
+            tcq_trailing_rs<true, 4 * RPT>(sh, a_g, lda, j0 + TCQ_NB, n, j0, mj, ldv
 #ifdef GPUB_TCQ_PROFILE
-                         , tcq_t0
+                                           , tcq_t0
 #endif
             );
             __syncthreads();
@@ -889,9 +1018,9 @@ __global__ void __launch_bounds__(TCQ_THREADS, 1) k_ormqr_tc(int m, int ncols, i
             }
             if (tid < TCQ_NB) sh.taus()[tid] = tid < nb ? tau_g[j0 + tid] : 0.0;
             __syncthreads();
-            tcq_trailing<TRANS>(sh, c_g, ldc, col0, col_end, j0, mj, ldv
+            tcq_trailing_rs<TRANS, 8>(sh, c_g, ldc, col0, col_end, j0, mj, ldv
 #ifdef GPUB_TCQ_PROFILE
-                                , tcq_t0
+                                      , tcq_t0
 #endif
             );
             __syncthreads();
@@ -1573,10 +1702,10 @@ int gels_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, T *A, size_t lda,
 extern "C" {
 
 #ifdef GPUB_TCQ_PROFILE
-int gpub_debug_tcq_profile(unsigned long long *out8, int reset) {
+int gpub_debug_tcq_profile(unsigned long long *out8, int reset) {   /* out8: 12 counters */
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, g_tcq_prof, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tcq_prof, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out8, g_tcq_prof, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_tcq_prof, z, sizeof(z)); }
     return 0;
 }
 #endif
