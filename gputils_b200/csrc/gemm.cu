@@ -365,11 +365,16 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // WARPS: 8 warps of 16 x 32 warp tiles (6 fragment loads per 8 DMMA) or 4 warps of 32 x 32 (8 per 16)
 // SYM (with TRB, A == B): C = A A^T is symmetric -- only the tiles on and below the diagonal are computed, each off-diagonal tile is
 // stored twice (itself and mirrored), which halves the flops of the Nullspace projector N N^T
-template<bool TRB, int DKT, int WARPS = 8, bool SYM = false>
+// PROJ (with TRB and SYM): the Nullspace projector P = N N^T from the orthogonal factor it is cut from. N = [ U(:, r:n) | 0 ], so
+// N N^T = U2 U2^T = I - U1 U1^T with U1 = U(:, 0:r): per matrix the kernel takes whichever side has FEWER columns (rank r read from
+// the device) -- A = N with k = n - r columns, or Ualt = U with k = r columns, alpha = -1 and the identity added in the epilogue.
+// For a fat 128 x 1024 matrix (r = 128) that is 128 instead of 896 columns: 7 x fewer flops for the same projector.
+template<bool TRB, int DKT, int WARPS = 8, bool SYM = false, bool PROJ = false>
 __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
-                                                    size_t tiles_n, size_t batch) {
+                                                    size_t tiles_n, size_t batch, const unsigned *__restrict__ rank = nullptr,
+                                                    const double *__restrict__ Ualt = nullptr, size_t sU = 0) {
     // As[buf][kk][row] (A panel, 16 x 64), Bs[buf][col][kk] (B panel stored k-contiguous per column)
     constexpr int BROWS = TRB ? DKT : 64, BLD = TRB ? DLD : DKT + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -394,6 +399,18 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
         }
         const double *a = A + b * sA + row0;
         const double *bb = B + b * sB + (TRB ? col0 : col0 * ldb);
+        size_t kcount = k;
+        bool comp = false;
+        if (PROJ) {
+            const size_t r = rank[b] < n ? rank[b] : n;
+            comp = r <= n - r;
+            kcount = comp ? r : n - r;
+            if (comp) {
+                a = Ualt + b * sU + row0;
+                bb = Ualt + b * sU + col0;
+            }
+            alpha = comp ? -1.0 : 1.0;
+        }
         double acc[MI][4][2];
 #pragma unroll
         for (int i = 0; i < MI; i++)
@@ -423,8 +440,8 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
             cp_async_commit();
         };
 
-        const size_t npan = k / DKT;
-        load_panel(0, 0);
+        const size_t npan = PROJ ? (kcount + DKT - 1) / DKT : k / DKT;
+        if (npan > 0) load_panel(0, 0);
         for (size_t p = 0; p < npan; p++) {
             const int buf = (int) (p & 1);
             if (p + 1 < npan) {
@@ -434,6 +451,15 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
                 cp_async_wait<0>();
             }
             __syncthreads();
+            if (PROJ && comp && p + 1 == npan && kcount % DKT != 0) {
+                // the columns of U beyond the rank that came along with the last panel do not belong to U1
+                const int kv = (int) (kcount % DKT);
+                for (int e = threadIdx.x; e < (DKT - kv) * 64; e += NTH) {
+                    As[buf][kv + e / 64][e % 64] = 0.0;
+                    Bs[buf][kv + e / 64][e % 64] = 0.0;
+                }
+                __syncthreads();
+            }
 #pragma unroll
             for (int k4 = 0; k4 < DKT; k4 += 4) {
                 double af[MI], bf[4];
@@ -457,7 +483,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
                 size_t gc = col0 + wc + 8 * j + 2 * q; // C fragment: row g, cols 2q, 2q+1
                 double *p0 = c + gr + gc * ldc;
                 double *p1 = p0 + ldc;
-                if (beta == 0.0) {
+                if (PROJ) {
+                    *p0 = alpha * acc[i][j][0] + ((comp && gr == gc) ? 1.0 : 0.0);
+                    *p1 = alpha * acc[i][j][1] + ((comp && gr == gc + 1) ? 1.0 : 0.0);
+                } else if (beta == 0.0) {
                     *p0 = alpha * acc[i][j][0];
                     *p1 = alpha * acc[i][j][1];
                 } else {
@@ -1090,6 +1119,19 @@ bool try_aat_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const d
     return true;
 }
 
+template<typename T>
+bool try_projector_dmma(gpub_ctx_t, cudaStream_t, size_t, const T *, size_t, const unsigned *, const T *, size_t, T *, size_t, size_t) { return false; }
+template<>
+bool try_projector_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *U, size_t sU, const unsigned *rank, const double *N,
+                                size_t sN, double *P, size_t sP, size_t batch) {
+    if (n % 64 != 0 || (sN & 1) || (sU & 1) || ((((uintptr_t) N) | ((uintptr_t) U)) & 15u)) return false;
+    const size_t tm = n / 64, total = tm * (tm + 1) / 2 * batch, cap = (size_t) ctx->sm_count * 8;
+    constexpr size_t smemT = sizeof(double) * (2 * 16 * DLD + 2 * 16 * DLD);
+    k_gemm_dmma<true, 16, 8, true, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP,
+                                                                                                         tm, tm, batch, rank, U, sU);
+    return true;
+}
+
 } // namespace
 
 extern "C" {
@@ -1120,5 +1162,19 @@ int gpub_gemm_batched_f32(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k
     }
 GPUB_DEF_AAT(f64, double)
 GPUB_DEF_AAT(f32, float)
+
+#define GPUB_DEF_PROJ(SUF, T)                                                                                        \
+    int gpub_nullspace_projector_batched_##SUF(gpub_ctx_t ctx, int sidx, size_t n, const T *U, size_t sU, const unsigned int *rank, \
+                                               const T *N, size_t sN, T *P, size_t sP, size_t batch) {               \
+        if (n == 0 || batch == 0) return GPUB_OK;                                                                    \
+        if (!N || !P || !U || !rank) return GPUB_EINVAL;                                                             \
+        {                                                                                                            \
+            GPUB_ENTER(ctx, sidx);                                                                                   \
+            if (try_projector_dmma<T>(ctx, stream, n, U, sU, rank, N, sN, P, sP, batch)) { GPUB_LAUNCH_CHECK(); return GPUB_OK; } \
+        }                                                                                                            \
+        return gpub_aat_batched_##SUF(ctx, sidx, n, N, sN, P, sP, batch);                                            \
+    }
+GPUB_DEF_PROJ(f64, double)
+GPUB_DEF_PROJ(f32, float)
 
 } // extern "C"

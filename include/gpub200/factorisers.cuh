@@ -335,7 +335,9 @@ inline Nullspace<T>::Nullspace(DTensor<T> &a) {
     /* N_i = last (n - rank_i) columns of U_i, moved to the front, zero elsewhere; then N_i N_i' */
     gpuErrChk(gpub200::Abi<T>::nullspace_pack(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(),
                                               n * n, nMats));
-    gpuErrChk(gpub200::Abi<T>::aat(gpub200::ctx(), s, n, m_nullspace->raw(), n * n, m_projOp->raw(), n * n, nMats));
+    /* N N' = I - U1 U1': the side with fewer columns is multiplied out, per matrix */
+    gpuErrChk(gpub200::Abi<T>::projector(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(), n * n,
+                                         m_projOp->raw(), n * n, nMats));
     /* U and the rank tensor die with `svd` at scope exit: wait for the two launches that read them */
     Session::getInstance().synchronizeStream(aTranspose.streamIdx());
 }

@@ -240,6 +240,16 @@ int gpub_aat_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *N, si
 int gpub_aat_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *N, size_t strideN,
                          float *P, size_t strideP, size_t batch);
 
+/* The same projector from the orthogonal factor N_i was cut out of: N_i N_i^T = U2 U2^T = I - U1 U1^T (U1 = the first rank_i columns
+ * of U_i), so per matrix the side with FEWER columns is multiplied out (rank read from the device). Same result as
+ * gpub_aat_batched up to rounding; for a fat 128 x 1024 matrix 7 x fewer flops. */
+int gpub_nullspace_projector_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *U, size_t strideU,
+                                         const unsigned int *rank, const double *N, size_t strideN,
+                                         double *P, size_t strideP, size_t batch);
+int gpub_nullspace_projector_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *U, size_t strideU,
+                                         const unsigned int *rank, const float *N, size_t strideN,
+                                         float *P, size_t strideP, size_t batch);
+
 /* ---- synthetic data (bench / tests): counter-based generator, SURVEY 8(d) ---
  * x[i] = lo + (hi - lo) * u(seed, i),  u in [0,1) from a 64-bit hash of i     */
 int gpub_fill_uniform_f64(gpub_ctx_t ctx, int sidx, size_t n, double *x, double lo, double hi, uint64_t seed);

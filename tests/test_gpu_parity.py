@@ -357,3 +357,26 @@ def test_padded_strides_are_accepted(gpu_ctx, oracle, n, batch, ld, pad):
     x = rhs.cpu().numpy()
     assert rel_err(x[:, :n, None], oracle.potrs_batched(Lo, b)) <= 2e-11
     assert np.all(x[:, n:] == 555.0)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n", [6, 64, 192])
+def test_nullspace_projector_from_the_orthogonal_factor(gpu_ctx, dt, n):
+    """gpub_nullspace_projector_batched: N N' computed as U2 U2' or as I - U1 U1', whichever side has fewer columns (rank read
+    from the device, any value in 0..n, not a multiple of the panel depth) == gpub_aat_batched on the packed basis."""
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(n)
+    ranks = np.array([0, 1, n // 2 - 1, n // 2, n // 2 + 1, n - 17 if n > 17 else 2, n - 1, n, 13 % n, 16 % n], dtype=np.int32)
+    batch = len(ranks)
+    U = np.linalg.qr(rng.uniform(-1, 1, (batch, n, n)))[0].astype(dt)
+    dU = dev(U); dr = torch.from_numpy(ranks).cuda()
+    dN = torch.empty_like(dU); dP = torch.full_like(dU, float("nan")); dP2 = torch.empty_like(dU)
+    gpu_ctx.call("nullspace_pack_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, batch)
+    gpu_ctx.call("nullspace_projector_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, capi._p(dP), n * n, batch)
+    gpu_ctx.call("aat_batched", dU, n, capi._p(dN), n * n, capi._p(dP2), n * n, batch)
+    P, P2, N = host(dP).astype(np.float64), host(dP2).astype(np.float64), host(dN).astype(np.float64)
+    tol = 20 * TOL[np.dtype(dt)]
+    assert np.abs(P - N @ N.transpose(0, 2, 1)).max() <= tol and np.abs(P - P2).max() <= tol
+    assert np.array_equal(P, P.transpose(0, 2, 1))
+    assert np.abs(P[0] - np.eye(n)).max() <= tol and np.abs(P[7]).max() <= tol     # rank 0: identity; full rank: zero
