@@ -406,6 +406,125 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Left factor of R without accumulating the rotations: the Jacobi kernel ends with R' J = W D, so J = R W D^-1 -- one small GEMM
+// (R W, tensor pipe) plus this kernel, instead of rotating a second n x n matrix in global memory through every sweep (which doubled
+// the kernel's time: there is no room for J next to X in shared memory at n = 128). Column i of R W divided by sigma_i is accurate to
+// eps * sigma_1 / sigma_i, so that is used while sigma_i >= weak * sigma_1; the columns behind (sorted: a suffix) carry little or no
+// information about R and only have to complete the orthonormal basis: each starts from its own (normalised) R w_i, or from the unit
+// vector least represented so far when that has no length left, and is orthogonalised twice against everything before it.
+// One CTA per matrix, the matrix in shared memory.
+// ------------------------------------------------------------------------------------------
+template<typename T>
+__global__ void __launch_bounds__(256) k_ur_finish(int n, T *Ur, size_t sUr, const T *__restrict__ S, size_t sS, size_t batch, int ldx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *X = reinterpret_cast<T *>(smem_raw);            // [n][ldx] columns
+    T *s_coef = X + (size_t) n * ldx;                   // [n]
+    __shared__ T s_val[8];
+    __shared__ int s_idx[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = 8, NT = 256;
+    const T weak = sizeof(T) == 8 ? T(1e-3) : T(1e-2);
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *u = Ur + mat * sUr;
+        const T *sg = S + mat * sS;
+        const T smax = sg[0];
+        int ngood = 0;
+        for (int i = 0; i < n; i++) ngood += (sg[i] >= weak * smax && sg[i] > T(0)) ? 1 : 0;   // sorted: a prefix
+        for (int e = tid; e < n * n; e += NT) {
+            const int r = e % n, c = e / n;
+            T v = u[e];
+            if (c < ngood) v *= T(1) / sg[c];
+            X[(size_t) c * ldx + r] = v;
+        }
+        __syncthreads();
+        auto cta_sum = [&](T v) {
+            v = jwarp_sum(v);
+            if (lane == 0) s_val[warp] = v;
+            __syncthreads();
+            T tot = 0;
+            for (int w = 0; w < NW; w++) tot += s_val[w];
+            __syncthreads();
+            return tot;
+        };
+        auto project_twice = [&](T *xz, int i) {
+            for (int pass = 0; pass < 2; pass++) {
+                for (int w = warp; w < i; w += NW) {
+                    const T *xw = X + (size_t) w * ldx;
+                    T g = 0;
+                    for (int r = lane; r < n; r += 32) g = fma(xw[r], xz[r], g);
+                    g = jwarp_sum(g);
+                    if (lane == 0) s_coef[w] = g;
+                }
+                __syncthreads();
+                for (int r = tid; r < n; r += NT) {
+                    T acc = xz[r];
+                    for (int w = 0; w < i; w++) acc = fma(-s_coef[w], X[(size_t) w * ldx + r], acc);
+                    xz[r] = acc;
+                }
+                __syncthreads();
+            }
+        };
+        for (int i = ngood; i < n; i++) {
+            T *xz = X + (size_t) i * ldx;
+            T nn = 0;
+            for (int r = tid; r < n; r += NT) nn = fma(xz[r], xz[r], nn);
+            nn = cta_sum(nn);
+            bool own = nn > T(0);
+            if (own) {
+                const T inv = T(1) / sqrt(nn);
+                for (int r = tid; r < n; r += NT) xz[r] *= inv;
+                __syncthreads();
+                project_twice(xz, i);
+                T n2 = 0;
+                for (int r = tid; r < n; r += NT) n2 = fma(xz[r], xz[r], n2);
+                n2 = cta_sum(n2);
+                own = n2 > T(0.25);                     // otherwise R w_i lies (numerically) in the span of the columns before it
+                if (own) {
+                    const T inv2 = T(1) / sqrt(n2);
+                    for (int r = tid; r < n; r += NT) xz[r] *= inv2;
+                    __syncthreads();
+                }
+            }
+            if (!own) {
+                // the unit vector with the largest component outside the span of the columns so far: 1 - sum_w w[k]^2
+                T best = T(-1);
+                int bestk = 0;
+                for (int k = tid; k < n; k += NT) {
+                    T acc = T(1);
+                    for (int w = 0; w < i; w++) {
+                        const T x = X[(size_t) w * ldx + k];
+                        acc = fma(-x, x, acc);
+                    }
+                    if (acc > best) { best = acc; bestk = k; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+                    if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+                }
+                if (lane == 0) { s_val[warp] = best; s_idx[warp] = bestk; }
+                __syncthreads();
+                best = s_val[0]; bestk = s_idx[0];
+                for (int w = 1; w < NW; w++)
+                    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bestk)) { best = s_val[w]; bestk = s_idx[w]; }
+                __syncthreads();
+                for (int r = tid; r < n; r += NT) xz[r] = (r == bestk) ? T(1) : T(0);
+                __syncthreads();
+                project_twice(xz, i);
+                T n2 = 0;
+                for (int r = tid; r < n; r += NT) n2 = fma(xz[r], xz[r], n2);
+                n2 = cta_sum(n2);
+                const T inv2 = T(1) / sqrt(n2);
+                for (int r = tid; r < n; r += NT) xz[r] *= inv2;
+                __syncthreads();
+            }
+        }
+        for (int e = tid; e < n * n; e += NT) u[e] = X[(size_t) (e / n) * ldx + (e % n)];
+        __syncthreads();
+    }
+}
+
 template<typename T> int internal_geqrf(gpub_ctx_t, int, size_t, size_t, T *, size_t, size_t, T *, size_t, size_t);
 template<> int internal_geqrf<double>(gpub_ctx_t c, int s, size_t m, size_t n, double *A, size_t lda, size_t sA, double *tau, size_t sT, size_t b) { return gpub_geqrf_batched_f64(c, s, m, n, A, lda, sA, tau, sT, b); }
 template<> int internal_geqrf<float>(gpub_ctx_t c, int s, size_t m, size_t n, float *A, size_t lda, size_t sA, float *tau, size_t sT, size_t b) { return gpub_geqrf_batched_f32(c, s, m, n, A, lda, sA, tau, sT, b); }
@@ -428,7 +547,7 @@ int internal_transpose(gpub_ctx_t c, int s, size_t m, size_t n, const float *A, 
     return gpub_transpose_batched_f32(c, s, m, n, A, sA, At, sAt, b);
 }
 
-inline size_t per_matrix_work_elems(size_t n) { return 2 * n * n + 8 * n + 8; }
+inline size_t per_matrix_work_elems(size_t n) { return 3 * n * n + 8 * n + 8; }
 
 // U = Q blockdiag(Ur, I) through one block reflector (see k_make_v / k_tfactor): fp64 shapes the tensor-pipe GEMM tiles cover
 template<typename T>
@@ -477,7 +596,7 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         return GPUB_OK;
     }
     if (n > 32) {
-        // jacobi path: per-matrix scratch = [Ur n*n | tau n]
+        // jacobi path: per-matrix scratch = [Ur n*n | tau n | R, later V(0:n)' Ur n*n | W n*n]
         const size_t ldx = n | 1;
         const size_t smem = (n * ldx + 2 * n) * sizeof(T) + n * sizeof(int) + 64;
         if (smem > (size_t) ctx->max_smem_optin - 2048) return GPUB_ENOTSUP;
@@ -486,10 +605,13 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         if (e) return e;
         const size_t cap = (size_t) ctx->sm_count * 2;
         const unsigned jgrid = (unsigned) (batch < cap ? batch : cap);
+        // the left factor of R comes from R W D^-1 afterwards (k_ur_finish) unless Vt is strided: then the rotations are accumulated
+        const size_t usm = (n * ldx + n) * sizeof(T);
+        const bool accumulate = want_u && (ldvt != n || usm > (size_t) ctx->max_smem_optin - 1024);
 #define GPUB_JACOBI_LAUNCH(JEV)                                                                                              \
     {                                                                                                                         \
         GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_rt<T, JEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));         \
-        k_jacobi_rt<T, JEV><<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, want_u ? 1 : 0, info, \
+        k_jacobi_rt<T, JEV><<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, accumulate ? 1 : 0, info, \
                                                          batch, (int) ldx);                                                   \
     }
         if (n <= 128) GPUB_JACOBI_LAUNCH(4)
@@ -498,6 +620,20 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         else return GPUB_ENOTSUP;
 #undef GPUB_JACOBI_LAUNCH
         GPUB_LAUNCH_CHECK();
+        if (want_u && !accumulate) {
+            T *Rw = w + n * n + n, *Ww = Rw + n * n;
+            const unsigned gr = (unsigned) (gpub_ceil_div(n * n * batch, 256) < 4096 ? gpub_ceil_div(n * n * batch, 256) : 4096);
+            k_extract_r<T><<<gr, 256, 0, stream>>>((int) n, A, lda, sA, Rw, per, batch);
+            GPUB_LAUNCH_CHECK();
+            e = internal_transpose(ctx, sidx, n, n, Vt, sVt, Ww, per, batch);                                           // W = Vt'
+            if (e) return e;
+            e = internal_gemm(ctx, sidx, n, n, n, T(1), Rw, n, per, Ww, n, per, T(0), Urj, n, per, batch);               // R W = J D
+            if (e) return e;
+            GPUB_CUDA(cudaFuncSetAttribute(k_ur_finish<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) usm));
+            k_ur_finish<T><<<(unsigned) (batch < (size_t) ctx->sm_count * 2 ? batch : (size_t) ctx->sm_count * 2), 256, usm, stream>>>(
+                (int) n, Urj, per, S, sS, batch, (int) ldx);
+            GPUB_LAUNCH_CHECK();
+        }
         if (want_u) {
             size_t total = m * m * batch;
             unsigned grid = (unsigned) (gpub_ceil_div(total, 256) < 8192 ? gpub_ceil_div(total, 256) : 8192);
