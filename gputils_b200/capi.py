@@ -36,6 +36,8 @@ _TYPED = {
     "axpy": [_sz, "T", _vp, _vp],
     "rot": [_sz, _vp, _sz, _vp, _sz, _vp, _vp, _int],
     "givens_rhypot": [_vp, _vp, _sz, _sz, _sz, _sz],
+    "rot_batched": [_sz, _vp, _sz, _vp, _sz, _sz, _vp, _vp, _sz],
+    "givens_annihilate_batched": [_vp, _sz, _sz, _sz, _sz, _sz, _sz, _sz],
     "gather_rows": [_vp, _sz, _sz, _sz, _sz, _vp],
     "transpose_batched": [_sz, _sz, _vp, _sz, _vp, _sz, _sz],
     "gemm_batched": [_sz, _sz, _sz, "T", _vp, _sz, _sz, _vp, _sz, _sz, "T", _vp, _sz, _sz, _sz],

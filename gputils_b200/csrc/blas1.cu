@@ -287,6 +287,47 @@ __global__ void k_rot(size_t n, T *x, size_t incx, T *y, size_t incy, const T *d
     }
 }
 
+// Batched Givens (additive; the reference's rot / GivensAnnihilator take one matrix, tensor.cuh:1074-1104, 2211-2312).
+// k_rot_batched: the same plane rotation of two strided vectors in EVERY matrix of a batch, (c, s) per matrix from device arrays.
+// k_givens_annihilate_batched: per matrix, G(i, k) that zeroes element (k, j): {rhypot, cos, -sin} from elements (i, j), (k, j)
+// exactly as k_givensAnnihilateRHypot (tensor.cuh:2272-2281), then rows i and k rotated -- one warp per matrix, one launch per
+// batch instead of a 1-thread kernel plus a cuBLAS call per matrix.
+template<typename T>
+__global__ void k_rot_batched(size_t n, T *x, size_t incx, T *y, size_t incy, size_t stride, const T *__restrict__ c, const T *__restrict__ s,
+                              size_t batch) {
+    const size_t total = n * batch;
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t) gridDim.x * blockDim.x) {
+        const size_t b = e / n, i = e - b * n;
+        const T cc = c[b], ss = s[b];
+        T *xp = x + b * stride + i * incx, *yp = y + b * stride + i * incy;
+        const T xi = *xp, yi = *yp;
+        *xp = cc * xi + ss * yi;
+        *yp = cc * yi - ss * xi;
+    }
+}
+
+template<typename T> __device__ __forceinline__ T dev_rhypot(T a, T b);
+template<> __device__ __forceinline__ double dev_rhypot<double>(double a, double b) { return rhypot(a, b); }
+template<> __device__ __forceinline__ float dev_rhypot<float>(float a, float b) { return rhypotf(a, b); }
+
+template<typename T>
+__global__ void k_givens_annihilate_batched(T *A, size_t nrows, size_t ncols, size_t stride, size_t i, size_t k, size_t j, size_t batch) {
+    const size_t warp = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    for (size_t b = warp; b < batch; b += nwarps) {
+        T *a = A + b * stride;
+        const T xij = a[i + j * nrows], xkj = a[k + j * nrows];
+        const T rh = dev_rhypot<T>(xij, xkj);
+        const T c = xij * rh, s = xkj * rh;
+        __syncwarp();                                      // every lane has read the pivot pair before column j is rotated
+        for (size_t col = lane; col < ncols; col += 32) {
+            const T xi = a[i + col * nrows], xk = a[k + col * nrows];
+            a[i + col * nrows] = c * xi + s * xk;
+            a[k + col * nrows] = c * xk - s * xi;
+        }
+    }
+}
+
 template<typename T>
 int rot(gpub_ctx_t ctx, int sidx, size_t n, T *x, size_t incx, T *y, size_t incy, const T *c, const T *s, int on_dev) {
     if (n == 0) return GPUB_OK;
@@ -482,6 +523,31 @@ int gpub_givens_rhypot_f32(gpub_ctx_t ctx, int sidx, const float *data, float *r
     GPUB_LAUNCH_CHECK();
     return GPUB_OK;
 }
+
+#define GPUB_DEF_GIVENS_BATCHED(SUF, T)                                                                                \
+    int gpub_rot_batched_##SUF(gpub_ctx_t ctx, int sidx, size_t n, T *x, size_t incx, T *y, size_t incy, size_t stride, \
+                               const T *c, const T *s, size_t batch) {                                                 \
+        if (n == 0 || batch == 0) return GPUB_OK;                                                                      \
+        if (!x || !y || !c || !s) return GPUB_EINVAL;                                                                  \
+        GPUB_ENTER(ctx, sidx);                                                                                         \
+        const size_t want = gpub_ceil_div(n * batch, 256);                                                             \
+        k_rot_batched<T><<<(unsigned) (want < 4096 ? want : 4096), 256, 0, stream>>>(n, x, incx, y, incy, stride, c, s, batch); \
+        GPUB_LAUNCH_CHECK();                                                                                           \
+        return GPUB_OK;                                                                                                \
+    }                                                                                                                  \
+    int gpub_givens_annihilate_batched_##SUF(gpub_ctx_t ctx, int sidx, T *A, size_t nrows, size_t ncols, size_t stride, \
+                                             size_t i, size_t k, size_t j, size_t batch) {                             \
+        if (batch == 0 || ncols == 0) return GPUB_OK;                                                                  \
+        if (!A || i >= nrows || k >= nrows || j >= ncols || i == k) return GPUB_EINVAL;                                \
+        GPUB_ENTER(ctx, sidx);                                                                                         \
+        const size_t want = gpub_ceil_div(batch, 8);                                                                   \
+        const size_t cap = (size_t) ctx->sm_count * 8;                                                                 \
+        k_givens_annihilate_batched<T><<<(unsigned) (want < cap ? want : cap), 256, 0, stream>>>(A, nrows, ncols, stride, i, k, j, batch); \
+        GPUB_LAUNCH_CHECK();                                                                                           \
+        return GPUB_OK;                                                                                                \
+    }
+GPUB_DEF_GIVENS_BATCHED(f64, double)
+GPUB_DEF_GIVENS_BATCHED(f32, float)
 
 #define GPUB_DEF_GATHER(SUF, T)                                                                                        \
     int gpub_gather_rows_##SUF(gpub_ctx_t ctx, int sidx, const T *src, size_t ld, size_t row_from, size_t nr, size_t nc, \

@@ -56,12 +56,9 @@ template<> __device__ __forceinline__ float fast_rcp<float>(float d) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
     return fmaf(y, fmaf(-d, y, 1.0f), y);
 }
-// GPUB_DIAG_TILED = 1: 4-column steps with the 4 x 4 diagonal tile factorised redundantly in every lane (see factor_diag in
-// k_potrf_blk). Measured slower (n = 128: fp64 0.86 -> 1.06 ms, fp32 1.17 -> 1.36 ms): the chain per column is shorter, but the
-// diagonal warp runs alone and its time is set by its instruction count (2180 instead of 1440 per 32 x 32 block, ~5 cycles each).
-#ifndef GPUB_DIAG_TILED
-#define GPUB_DIAG_TILED 0
-#endif
+// (Measured and rejected for the diagonal blocks of the blocked kernel: 4-column steps with the 4 x 4 diagonal tile factorised
+// redundantly in every lane -- n = 128: fp64 0.86 -> 1.06 ms, fp32 1.17 -> 1.36 ms. The chain per column is shorter, but the diagonal
+// warp runs alone and its time is set by its instruction count: 2180 instead of 1440 per 32 x 32 block, ~5 cycles each.)
 
 // ------------------------------------------------------------------------------------------
 // potrf, n <= 32: NP lanes per matrix
@@ -265,7 +262,7 @@ __global__ void __launch_bounds__(128) k_potrs8_f32(const float *__restrict__ L,
 #define GPUB_POTRF32_MINB 4
 #endif
 // N = 64, 32 or 16: H = N / 2 lanes per matrix, lane p owns rows p and p + H. N = 64 is a whole warp per matrix with the
-// lower triangle in registers (96 entries per lane): no CTA barrier at all, which is what k_potrf_blk loses its time on.
+// lower triangle in registers (96 entries per lane): no CTA barrier at all (a 32 x 32-block kernel with one warp per block lost its time there).
 // DENSE: n == N and lda == N; otherwise rows / columns beyond n are an identity pad and lda is a run-time value.
 #ifndef GPUB_CHOL4
 #define GPUB_CHOL4 1
@@ -347,25 +344,12 @@ __global__ void __launch_bounds__(128, PotrfPairMinB<T, N, DENSE>::value) k_potr
 }
 
 // ------------------------------------------------------------------------------------------
-// potrf, 32 < n <= 32*NB (NB = 2, 3, 4): k_potrf_blk<T, NB>, one matrix per CTA.
-// The matrix is cut into 32 x 32 blocks; one warp owns one block of the lower triangle for the whole
-// factorisation (lane = row of the block, the 32 entries of that row in registers). Blocked right-looking:
-//   for each block column hb:
-//     (1) the diagonal warp factorises its block exactly like k_potrf_group (shuffled pivot, rsqrt, column
-//         broadcast through shared memory) and leaves L11 and the reciprocal pivots in shared memory;
-//     (2) the warps below solve L21 = A21 L11^-T with no inter-lane dependency at all (every lane owns a row)
-//         and leave their block in shared memory, stored [k][row];
-//     (3) every trailing warp applies its rank-32 update a(row, c) -= sum_k L(row, k) L(c, k): its own row
-//         comes from the panel block of its block row (conflict-free), the other factor is a 128-bit
-//         broadcast from the panel block of its block column.
-// Three CTA barriers per block column instead of two per column. Rows / columns beyond n are an identity pad.
+// potrf, 64 < n <= 32*NB (NB = 3, 4): blocked right-looking factorisation, one matrix per CTA (k_potrf_pipe below).
+// The matrix is cut into 32 x 32 blocks; one warp owns one block of the lower triangle for the whole factorisation. For each
+// block column hb: the diagonal warp factorises its block (lane = row, shuffled pivot, rsqrt, column broadcast through shared
+// memory), the warps below solve L21 = A21 L11^-T with no inter-lane dependency (every lane owns a row), and every trailing warp
+// applies its rank-32 update. Rows / columns beyond n are an identity pad.
 // ------------------------------------------------------------------------------------------
-#ifdef GPUB_CHOL_PROFILE
-__device__ unsigned long long g_chol_prof[8];
-#define CHOL_T(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_chol_prof[idx], (unsigned long long) (t_ - cp_t0)); cp_t0 = t_; } } while (0)
-#else
-#define CHOL_T(idx) do { } while (0)
-#endif
 // resident CTAs per SM the register allocation is tuned for
 #ifndef GPUB_BLK4_F32_MINB
 #define GPUB_BLK4_F32_MINB 3
@@ -381,221 +365,19 @@ template<typename T, int NB> struct PotrfBlkMinB { static constexpr int value = 
 #ifndef GPUB_BLK_DMMA
 #define GPUB_BLK_DMMA 1
 #endif
-#ifndef GPUB_POTRF_PIPE
-#define GPUB_POTRF_PIPE 1
-#endif
 __device__ __forceinline__ void chol_dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template<typename T, int NB>
-__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>::value) k_potrf_blk(int n, T *A, size_t lda, size_t strideA, int *info, size_t batch) {
-    constexpr int NW = NB * (NB + 1) / 2;
-    constexpr bool FRAG = GPUB_BLK_DMMA && sizeof(T) == 8;   // trailing blocks in DMMA accumulator layout
-    constexpr int LDP = FRAG ? 36 : 32;                      // row stride of a panel slot
-    __shared__ __align__(16) T s_p[NB][32][LDP]; // panel blocks of the current block column: [block row][k][row]
-    __shared__ __align__(16) T s_d[32][LDP];     // factor of the current diagonal block, [k][row]
-    __shared__ T s_rinv[32];
-    __shared__ int s_bad;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, q = lane & 3;
-    // enumerate the lower-triangular blocks: warp -> (rb, h), rb >= h
-    int rb = 0;
-    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
-    const int h = warp - rb * (rb + 1) / 2;
-    const int row = 32 * rb + lane;
-
-#ifdef GPUB_CHOL_PROFILE
-    long long cp_t0 = clock64();
-#endif
-    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
-        T *a_g = A + mat * strideA;
-        T a[32];
-        // accumulator tiles -> lane = row, through a scratch slot nobody reads at that time
-        auto to_rows = [&](T *scr) {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) scr[(8 * j + 2 * q + e) * LDP + 8 * i + g] = a[(4 * i + j) * 2 + e];
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 32; c++) a[c] = scr[c * LDP + lane];
-            __syncwarp();
-        };
-        // The diagonal warp of block column hb: 32 x 32 factorisation in 4-column steps, factor and reciprocal pivots left in shared
-        // memory. The serial chain of a column-by-column factorisation is pivot shuffle -> rsqrt -> scale -> broadcast (~240 cycles
-        // per column with nine warps waiting). Here the 4 x 4 diagonal tile of a step is gathered into EVERY lane (10 shuffles in
-        // flight together) and factorised redundantly in registers: the pivots follow the LDL^T recurrence d_k = D_kk - sum u_kj^2 / d_j
-        // through reciprocals, so the four rsqrt (for the L entries) hang off the chain instead of sitting in it; each lane then
-        // solves its own row against the tile and one shared-memory round publishes the 4 columns for the rank-4 update.
-        auto factor_diag = [&](int hb) {
-            int bad = 0;
-#if GPUB_DIAG_TILED
-            auto tile_step = [&](auto c0_tag) {
-                constexpr int c0 = decltype(c0_tag)::value;
-                T D[4][4];
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-#pragma unroll
-                    for (int r = c; r < 4; r++) D[r][c] = __shfl_sync(0xffffffffu, a[c0 + c], c0 + r);
-                // unnormalised columns u (in place in D), pivots d_k on the diagonal, reciprocals iv, rsqrt rs
-                T iv[4], rs[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (!(D[k][k] > T(0)) && bad == 0) bad = c0 + k + 1;
-                    iv[k] = fast_rcp<T>(D[k][k]);
-                    rs[k] = fast_rsqrt<T>(D[k][k]);
-#pragma unroll
-                    for (int c = k + 1; c < 4; c++) {
-                        const T m = D[c][k] * iv[k];
-#pragma unroll
-                        for (int r = c; r < 4; r++) D[r][c] = fma(-D[r][k], m, D[r][c]);
-                    }
-                }
-                // this lane's row against the tile: x_c = (a_c - sum_{k<c} x_k l_ck) / l_cc with l_ck = u_ck rs_k
-                T x[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    T acc = a[c0 + c];
-#pragma unroll
-                    for (int k = 0; k < c; k++) acc = fma(-x[k], D[c][k] * rs[k], acc);
-                    x[c] = acc * rs[c];
-                    a[c0 + c] = x[c];
-                    s_d[c0 + c][lane] = x[c];
-                }
-                if (lane < 4) s_rinv[c0 + lane] = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
-                __syncwarp();
-#pragma unroll
-                for (int c = c0 + 4; c < 32; c++) {
-                    T acc = a[c];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) acc = fma(-x[k], s_d[c0 + k][c], acc);
-                    a[c] = acc;
-                }
-            };
-            // explicit unrolling: every index into a[] must be a compile-time constant to stay in registers
-            tile_step(std::integral_constant<int, 0>{}); tile_step(std::integral_constant<int, 4>{});
-            tile_step(std::integral_constant<int, 8>{}); tile_step(std::integral_constant<int, 12>{});
-            tile_step(std::integral_constant<int, 16>{}); tile_step(std::integral_constant<int, 20>{});
-            tile_step(std::integral_constant<int, 24>{}); tile_step(std::integral_constant<int, 28>{});
-#else
-            T d = __shfl_sync(0xffffffffu, a[0], 0);   // pivot chain kept out of shared memory, see k_potrf_group
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (!(d > T(0)) && bad == 0) bad = j + 1;
-                const T r = fast_rsqrt<T>(d);
-                const T l = a[j] * r;
-                a[j] = l;
-                if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
-                s_d[j][lane] = l;
-                if (lane == j) s_rinv[j] = r;
-                __syncwarp();
-#pragma unroll
-                for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
-            }
-#endif
-            if (lane == 0 && bad != 0) atomicCAS(&s_bad, 0, 32 * hb + bad);   // block columns finish in order: the first one to fail wins
-        };
-        if (FRAG && h > 0) {
-            // accumulator layout: a[(4 i + j) * 2 + e] = entry (8 i + g, 8 j + 2 q + e) of the block
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int r_ = 32 * rb + 8 * i + g, c_ = 32 * h + 8 * j + 2 * q + e;
-                        a[(4 * i + j) * 2 + e] = (r_ < n && c_ <= r_) ? a_g[r_ + (size_t) c_ * lda] : T(r_ == c_ ? 1 : 0);
-                    }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int col = 32 * h + c;
-                a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
-            }
-        }
-        if (threadIdx.x == 0) s_bad = 0;
-        __syncthreads();
-        CHOL_T(0);
-        if (warp == 0) factor_diag(0);
-        __syncthreads();
-        CHOL_T(1);
-        // Per block column two barriers: (2) panel solves, then (3) trailing updates -- and the warp of the NEXT diagonal block
-        // factorises it as soon as its own update is done, while the other trailing warps are still updating (look-ahead).
-#pragma unroll 1
-        for (int hb = 0; hb + 1 < NB; hb++) {
-            if (h == hb && rb > hb) { // (2) panel blocks: rows below the diagonal block
-                if (FRAG && hb > 0) to_rows(&s_p[rb][0][0]);   // the block row's slot is free since the barrier that closed column hb - 1
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const T l = a[j] * s_rinv[j];
-                    a[j] = l;
-                    s_p[rb][j][lane] = l;
-#pragma unroll
-                    for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_d[j][c], a[c]);
-                }
-            }
-            __syncthreads();
-            CHOL_T(2);
-            if (h > hb) { // (3) trailing blocks (rb >= h > hb)
-                if constexpr (FRAG) {
-#pragma unroll 2
-                    for (int k4 = 0; k4 < 32; k4 += 4) {
-                        double af[4], bf[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) af[i] = -(double) s_p[rb][k4 + q][8 * i + g];   // A(row g, k q) = L(rb, hb)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) bf[j] = (double) s_p[h][k4 + q][8 * j + g];     // B(k q, col g) = L(h, hb)^T
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                double c0 = (double) a[(4 * i + j) * 2], c1 = (double) a[(4 * i + j) * 2 + 1];
-                                chol_dmma(c0, c1, af[i], bf[j]);
-                                a[(4 * i + j) * 2] = (T) c0;
-                                a[(4 * i + j) * 2 + 1] = (T) c1;
-                            }
-                    }
-                } else {
-#pragma unroll 8
-                    for (int k = 0; k < 32; k++) {
-                        const T lk = s_p[rb][k][lane];
-#pragma unroll
-                        for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[h][k][c], a[c]);
-                    }
-                }
-                if (rb == hb + 1 && h == hb + 1) {   // the next diagonal block is complete: factorise it now
-                    if (FRAG) to_rows(&s_d[0][0]);   // s_d was last read by the panel solves of column hb, which are behind a barrier
-                    factor_diag(hb + 1);
-                }
-            }
-            __syncthreads();
-            CHOL_T(3);
-        }
-        if (row < n) {
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int col = 32 * h + c;
-                if (col <= row) a_g[row + (size_t) col * lda] = a[c];
-            }
-        }
-        if (threadIdx.x == 0) info[mat] = s_bad;
-        __syncthreads();
-        CHOL_T(4);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// potrf, 64 < n <= 32*NB, PIPELINED version: k_potrf_pipe<T, NB>. Same block ownership, arithmetic and DMMA trailing update as
-// k_potrf_blk, but ONE CTA barrier per block column. In the interval of block column hb
+// k_potrf_pipe<T, NB>: ONE CTA barrier per block column (its predecessor had a barrier after each of the three phases). In the
+// interval of block column hb
 //   * every warp with h >= hb first applies the rank-32 update of block column hb - 1 to its block,
 //   * the diagonal warp (hb, hb) then factorises its block column by column and publishes its progress (a counter in shared
 //     memory, written after the column and its reciprocal pivot are in place),
 //   * the panel warps (rb > hb, hb) follow it one column behind: column j of the panel solve needs only column j of L11, so the
 //     panel solves finish ~100 cycles after the diagonal block instead of a whole phase later.
-// k_potrf_blk's stall samples were 72 % barrier waits, most of them nine warps waiting for the diagonal warp; here the panel
+// The three-barrier predecessor's stall samples were 72 % barrier waits, most of them nine warps waiting for the diagonal warp; here the panel
 // phase (18 % of a matrix) disappears from the critical path: per block column it is update + diagonal block.
 // The panel slots are double-buffered by block-column parity (the trailing warps of column hb - 1 still read L(., hb - 1) while
 // the panel warps of column hb write L(., hb)); the only spinning is the panel warps' poll of the progress counter, inside one
@@ -833,120 +615,6 @@ __global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfBlkMinB<T, NB>:
 }
 
 // ------------------------------------------------------------------------------------------
-// potrf, 32 < n <= 32*NB, DATAFLOW version: k_potrf_flow<T, NB>. Same block ownership and arithmetic as k_potrf_blk, but
-// no CTA barrier inside a matrix. Every finished block (diagonal factor or panel block) is published in its own shared-memory
-// slot with a per-block flag; warp (rb, h) first applies the updates of the block columns hb < h as their panel blocks
-// L(rb, hb) and L(h, hb) become available, then factorises (rb == h) or solves (rb > h) its own block and publishes it.
-// The chain diag(hb) -> panel(hb+1, hb) -> update of (hb+1, hb+1) -> diag(hb+1) is the only serial part; everything else
-// (the other panel blocks, the rest of the trailing update, the stores) overlaps with the next diagonal factorisation, which
-// k_potrf_blk cannot do: its phase timers show 40-50 % of a matrix's time in diagonal blocks with every other warp waiting.
-// ------------------------------------------------------------------------------------------
-template<typename T, int NB> struct PotrfFlowMinB { static constexpr int value = NB == 2 ? 5 : (NB == 3 ? 3 : 2); };
-
-#ifndef GPUB_FLOW_SLEEP
-#define GPUB_FLOW_SLEEP 20
-#endif
-__device__ __forceinline__ void flow_wait(const volatile int *flag, int epoch) {
-    while (*flag != epoch) __nanosleep(GPUB_FLOW_SLEEP);
-    __syncwarp();
-    __threadfence_block();
-}
-__device__ __forceinline__ void flow_post(volatile int *flag, int epoch, int lane) {
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        *flag = epoch;
-    }
-}
-
-template<typename T, int NB>
-__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrfFlowMinB<T, NB>::value) k_potrf_flow(int n, T *A, size_t lda, size_t strideA, int *info,
-                                                                                                          size_t batch) {
-    constexpr int NW = NB * (NB + 1) / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T (*s_p)[32][32] = reinterpret_cast<T (*)[32][32]>(smem_raw);   // [block id][k][row]: published blocks, one slot each
-    __shared__ T s_rinv[NB][32];
-    __shared__ int s_done[NW];
-    __shared__ int s_bad[2];   // by epoch parity: the slot of a matrix is reset after its info is written, a barrier before its reuse
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int rb = 0;
-    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
-    const int h = warp - rb * (rb + 1) / 2;
-    const int row = 32 * rb + lane;
-    if (threadIdx.x < NW) s_done[threadIdx.x] = 0;
-    if (threadIdx.x < 2) s_bad[threadIdx.x] = 0;
-    __syncthreads();
-    int epoch = 0;
-    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
-        epoch++;
-        T *a_g = A + mat * strideA;
-        T a[32];
-#pragma unroll
-        for (int c = 0; c < 32; c++) {
-            const int col = 32 * h + c;
-            a[c] = (row < n && col <= row) ? a_g[row + (size_t) col * lda] : T(row == col ? 1 : 0);
-        }
-        // updates from the block columns to the left
-#pragma unroll 1
-        for (int hb = 0; hb < h; hb++) {
-            const int idr = rb * (rb + 1) / 2 + hb, idc = h * (h + 1) / 2 + hb;   // L(rb, hb), L(h, hb)
-            flow_wait(&s_done[idr], epoch);
-            if (idc != idr) flow_wait(&s_done[idc], epoch);
-#pragma unroll 8
-            for (int k = 0; k < 32; k++) {
-                const T lk = s_p[idr][k][lane];
-#pragma unroll
-                for (int c = 0; c < 32; c++) a[c] = fma(-lk, s_p[idc][k][c], a[c]);
-            }
-        }
-        if (rb == h) { // diagonal block
-            int bad = 0;
-            T d = __shfl_sync(0xffffffffu, a[0], 0);
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (!(d > T(0)) && bad == 0) bad = j + 1;
-                const T r = fast_rsqrt<T>(d);
-                const T l = a[j] * r;
-                a[j] = l;
-                if (j + 1 < 32) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1 < 32 ? j + 1 : j]), j + 1);
-                s_p[warp][j][lane] = l;
-                if (lane == j) s_rinv[h][j] = r;
-                __syncwarp();
-#pragma unroll
-                for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[warp][j][c], a[c]);
-            }
-            if (lane == 0 && bad != 0 && s_bad[epoch & 1] == 0) s_bad[epoch & 1] = 32 * h + bad;
-            flow_post(&s_done[warp], epoch, lane);
-        } else { // panel block below the diagonal block of column h
-            const int idd = h * (h + 1) / 2 + h;
-            flow_wait(&s_done[idd], epoch);
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const T l = a[j] * s_rinv[h][j];
-                a[j] = l;
-                s_p[warp][j][lane] = l;
-#pragma unroll
-                for (int c = j + 1; c < 32; c++) a[c] = fma(-l, s_p[idd][j][c], a[c]);
-            }
-            flow_post(&s_done[warp], epoch, lane);
-        }
-        if (row < n) {
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int col = 32 * h + c;
-                if (col <= row) a_g[row + (size_t) col * lda] = a[c];
-            }
-        }
-        __syncthreads();   // every reader of this matrix's slots is done before the next matrix overwrites them
-        if (threadIdx.x == 0) {
-            info[mat] = s_bad[epoch & 1];
-            s_bad[epoch & 1] = 0;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // potrf, any n: one CTA per matrix (shared memory when it fits, else in place in global memory)
 // ------------------------------------------------------------------------------------------
 template<typename T>
@@ -1067,23 +735,6 @@ k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// potrs, 32 < n <= 32*NB (NB = 2, 3, 4): k_potrs_blk<T, NB>, one matrix per CTA, same block ownership as
-// k_potrf_blk: one warp per 32 x 32 block of the lower triangle, lane = row of the block, the 32 entries of
-// that row in registers, read once from global memory (lower triangle only, coalesced column-wise).
-//   forward  L y = b, block column hb ascending:
-//     diagonal warp : t = b_hb - sum of the partial products left by its row of blocks, then the row-scaled
-//                     substitution of k_potrs_group (one shuffle + one FMA per step);
-//     warps below   : p = L(rb, hb) y_hb, one per-lane dot product against the broadcast y (LDS.128);
-//   backward L^T x = y, block column hb descending:
-//     diagonal warp : u = y_hb - partials, substitution on the columns of D^-1 L (transposed once through a
-//                     padded shared tile), x = D^-1 v;
-//     warps left of it (rb == hb): q = L(hb, h)^T x_hb. Lane r holds row r, so the 32 column sums are formed
-//                     by a 5-stage transpose-reduce butterfly (31 shuffles) instead of a second, transposed read.
-// Two CTA barriers per block column and direction. Rows / columns beyond n are an identity pad.
-// ------------------------------------------------------------------------------------------
-template<typename T, int NB> struct PotrsBlkMinB { static constexpr int value = NB == 2 ? 6 : (NB == 3 ? 3 : 2); };
-
 // p[c] summed over the 32 lanes, result for c == lane
 template<typename T>
 __device__ __forceinline__ T transpose_reduce32(T (&p)[32], int lane) {
@@ -1098,110 +749,6 @@ __device__ __forceinline__ T transpose_reduce32(T (&p)[32], int lane) {
         }
     }
     return p[0];
-}
-
-template<typename T, int NB>
-__global__ void __launch_bounds__(32 * (NB * (NB + 1) / 2), PotrsBlkMinB<T, NB>::value)
-k_potrs_blk(int n, const T *__restrict__ L, size_t ldl, size_t strideL, T *b, size_t strideB, size_t batch) {
-    constexpr int NW = NB * (NB + 1) / 2;
-    __shared__ __align__(16) T s_x[NB * 32];      // right-hand side -> y -> x
-    __shared__ __align__(16) T s_part[NW][32];    // partial products, one slot per block
-    __shared__ T s_t[NB][32][33];                 // diagonal blocks of D^-1 L for the transposed read
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int rb = 0;
-    while ((rb + 1) * (rb + 2) / 2 <= warp) rb++;
-    const int h = warp - rb * (rb + 1) / 2;
-    const bool diag = rb == h;
-    const int row = 32 * rb + lane;
-    using V2 = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
-    constexpr int VN = 16 / sizeof(T);
-
-    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
-        const T *l_g = L + mat * strideL;
-        T *b_g = b + mat * strideB;
-        T l[32];
-#pragma unroll
-        for (int c = 0; c < 32; c++) {
-            const int col = 32 * h + c;
-            l[c] = (row < n && col <= row) ? l_g[row + (size_t) col * ldl] : T(row == col ? 1 : 0);
-        }
-        if (threadIdx.x < NB * 32) s_x[threadIdx.x] = threadIdx.x < n ? b_g[threadIdx.x] : T(0);
-        T dinv = T(1);
-        if (diag) {
-#pragma unroll
-            for (int c = 0; c < 32; c++)
-                if (c == lane) dinv = T(1) / l[c];
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                l[c] = c < lane ? l[c] * dinv : T(0);   // strictly lower part of D^-1 L
-                s_t[rb][lane][c] = l[c];
-            }
-        }
-        __syncthreads();
-        // ---- forward ----
-#pragma unroll 1
-        for (int hb = 0; hb < NB; hb++) {
-            if (diag && rb == hb) {
-                T x = s_x[32 * hb + lane];
-                for (int hp = 0; hp < hb; hp++) x -= s_part[hb * (hb + 1) / 2 + hp][lane];
-                x *= dinv;
-#pragma unroll
-                for (int j = 0; j < 31; j++) {
-                    const T yj = __shfl_sync(0xffffffffu, x, j);
-                    x = fma(-l[j], yj, x);
-                }
-                s_x[32 * hb + lane] = x;
-            }
-            __syncthreads();
-            if (h == hb && rb > hb) {
-                T p0 = 0, p1 = 0;
-#pragma unroll
-                for (int c = 0; c < 32; c += VN) {
-                    const V2 v = *reinterpret_cast<const V2 *>(&s_x[32 * hb + c]);
-                    T y[VN];
-                    if constexpr (sizeof(T) == 8) { y[0] = v.x; y[1] = v.y; }
-                    else { y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w; }
-#pragma unroll
-                    for (int e = 0; e < VN; e++) {
-                        if (e & 1) p1 = fma(l[c + e], y[e], p1);
-                        else p0 = fma(l[c + e], y[e], p0);
-                    }
-                }
-                s_part[warp][lane] = p0 + p1;
-            }
-            __syncthreads();
-        }
-        // ---- backward ----
-        if (diag) {
-#pragma unroll
-            for (int r = 0; r < 32; r++) l[r] = s_t[rb][r][lane]; // column `lane` of D^-1 L (zero on and above the diagonal)
-        }
-#pragma unroll 1
-        for (int hb = NB - 1; hb >= 0; hb--) {
-            if (diag && rb == hb) {
-                T x = s_x[32 * hb + lane];
-                for (int rp = hb + 1; rp < NB; rp++) x -= s_part[rp * (rp + 1) / 2 + hb][lane];
-#pragma unroll
-                for (int jj = 31; jj > 0; jj--) {
-                    const T vj = __shfl_sync(0xffffffffu, x, jj);
-                    x = fma(-l[jj], vj, x);
-                }
-                x *= dinv;
-                s_x[32 * hb + lane] = x;
-            }
-            __syncthreads();
-            if (rb == hb && h < hb) {
-                // each off-diagonal warp comes here exactly once per matrix, so its row can be consumed in place
-                const T xr = s_x[32 * hb + lane];
-#pragma unroll
-                for (int c = 0; c < 32; c++) l[c] *= xr;
-                s_part[warp][lane] = transpose_reduce32<T>(l, lane);
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x < n) b_g[threadIdx.x] = s_x[threadIdx.x];
-        __syncthreads();
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1326,7 +873,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : 4) k_potrs_pair64(in
 //   forward : warp 0 solves block 1 -> warps 1, 2: rhs2 -= Lb21 y1 (a 64-term dot product per lane against the broadcast y1)
 //             -> warp 3 solves block 2 forward AND backward;
 //   backward: warps 1, 2: Lb21^T v2 (64 per-lane products, two 31-shuffle transpose-reduce butterflies) -> warp 0 finishes.
-// Five CTA barriers per matrix instead of the sixteen of k_potrs_blk<T, 4>, and no warp ever waits inside a 32-column block.
+// Five CTA barriers per matrix instead of the sixteen of a 32 x 32-block kernel, and no warp ever waits inside a 32-column block.
 // ------------------------------------------------------------------------------------------
 // The four warps of k_potrs_quad128 play different roles and meet at the CTA barrier from their own branches (every thread executes
 // the same number of barriers). That is what named barriers are for at the PTX level (bar.sync id, count: warps may arrive from
@@ -1512,39 +1059,17 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
     } else if (n <= 128) {
         const size_t cap = (size_t) ctx->sm_count * 8;
         const unsigned grid = (unsigned) (batch < cap ? batch : cap);
-        // measured (profiles/r1d): the dataflow version wins for fp32 n <= 64 (1.49 vs 1.93 ms), the barrier version elsewhere
-        if (n <= 64 && sizeof(T) == 4) {
-            const size_t smem = (size_t) 3 * 32 * 32 * sizeof(T);
-            k_potrf_flow<T, 2><<<grid, 32 * 3, smem, stream>>>((int) n, A, lda, strideA, info, batch);
-        } else if (n <= 64) k_potrf_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, A, lda, strideA, info, batch);
-        else if (n <= 96) {
-#if GPUB_POTRF_PIPE
+        if (n <= 96) {
             constexpr int LDPH = (GPUB_BLK_DMMA && sizeof(T) == 8) ? 36 : 32;
             const size_t smem = sizeof(T) * ((size_t) (2 * 3 + 1) * 32 * LDPH + 32);
             GPUB_CUDA(cudaFuncSetAttribute(k_potrf_pipe<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             k_potrf_pipe<T, 3><<<grid, 32 * 6, smem, stream>>>((int) n, A, lda, strideA, info, batch);
-#else
-            k_potrf_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, A, lda, strideA, info, batch);
-#endif
-        }
-#ifdef GPUB_POTRF_FLOW128
-        else {
-            const size_t smem = (size_t) 10 * 32 * 32 * sizeof(T);
-            GPUB_CUDA(cudaFuncSetAttribute(k_potrf_flow<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            k_potrf_flow<T, 4><<<grid, 32 * 10, smem, stream>>>((int) n, A, lda, strideA, info, batch);
-        }
-#else
-        else {
-#if GPUB_POTRF_PIPE
+        } else {
             constexpr int LDPH = (GPUB_BLK_DMMA && sizeof(T) == 8) ? 36 : 32;
             const size_t smem = sizeof(T) * ((size_t) (2 * 4 + 1) * 32 * LDPH + 32);
             GPUB_CUDA(cudaFuncSetAttribute(k_potrf_pipe<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             k_potrf_pipe<T, 4><<<grid, 32 * 10, smem, stream>>>((int) n, A, lda, strideA, info, batch);
-#else
-            k_potrf_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, A, lda, strideA, info, batch);
-#endif
         }
-#endif
     } else {
         const size_t bytes = n * n * sizeof(T);
         const int use_smem = bytes <= (size_t) ctx->max_smem_optin - 1024 ? 1 : 0;
@@ -1609,14 +1134,7 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
     } else if (n <= 128) {
         const size_t cap = (size_t) ctx->sm_count * 8;
         const unsigned grid = (unsigned) (batch < cap ? batch : cap);
-#ifndef GPUB_POTRS_BLK128
         k_potrs_quad128<T><<<grid, 128, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
-        GPUB_LAUNCH_CHECK();
-        return GPUB_OK;
-#endif
-        if (n <= 64) k_potrs_blk<T, 2><<<grid, 32 * 3, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
-        else if (n <= 96) k_potrs_blk<T, 3><<<grid, 32 * 6, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
-        else k_potrs_blk<T, 4><<<grid, 32 * 10, 0, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);
     } else {
         const size_t smem = n * sizeof(T);
         if (smem > 48 * 1024)
@@ -1633,14 +1151,6 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
 
 extern "C" {
 
-#ifdef GPUB_CHOL_PROFILE
-int gpub_debug_chol_profile(unsigned long long *out8, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, g_chol_prof, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_prof, z, sizeof(z)); }
-    return 0;
-}
-#endif
 
 int gpub_potrf_batched_f64(gpub_ctx_t c, int s, size_t n, double *A, size_t lda, size_t sA, int *info, size_t b) { return potrf_batched<double>(c, s, n, A, lda, sA, info, b); }
 int gpub_potrf_batched_f32(gpub_ctx_t c, int s, size_t n, float *A, size_t lda, size_t sA, int *info, size_t b) { return potrf_batched<float>(c, s, n, A, lda, sA, info, b); }

@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
                         int p = -1, q = -1;
                         if (i < npad / 2) {
                             if (i == 0) { p = npad - 1; q = round; }
-                            else { p = (round + i) % (npad - 1); q = (round - i + (npad - 1)) % (npad - 1); }
+                            else {   // (round +- i) mod (npad - 1) without a division: both terms are below npad - 1
+                                p = round + i; p -= p >= npad - 1 ? npad - 1 : 0;
+                                q = round - i; q += q < 0 ? npad - 1 : 0;
+                            }
                             if (p >= n || q >= n) { p = -1; q = -1; }      // bye
                             else if (p > q) { const int t = p; p = q; q = t; }
                         }

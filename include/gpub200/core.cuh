@@ -294,6 +294,8 @@ template<typename T> struct Abi;
         static constexpr auto axpy = gpub_axpy_##SUF;                                                               \
         static constexpr auto rot = gpub_rot_##SUF;                                                                 \
         static constexpr auto rhypot = gpub_givens_rhypot_##SUF;                                                    \
+        static constexpr auto rot_batched = gpub_rot_batched_##SUF;                                                 \
+        static constexpr auto annihilate_batched = gpub_givens_annihilate_batched_##SUF;                            \
         static constexpr auto gather_rows = gpub_gather_rows_##SUF;                                                 \
         static constexpr auto transpose = gpub_transpose_batched_##SUF;                                             \
         static constexpr auto gemm = gpub_gemm_batched_##SUF;                                                       \

@@ -454,6 +454,50 @@ public:
     void annihilate(size_t i, size_t k, size_t j);
 };
 
+/**
+ * Additive API: Givens rotations on EVERY matrix of a tensor at once. The reference's applyLeft/RightGivensRotation and
+ * GivensAnnihilator refuse tensors (numMats > 1: tensor.cuh:1076, 1090, 2229, 2240), so a batch costs numMats x (a one-thread kernel +
+ * a cuBLAS rot); here annihilate() is one launch for the whole batch and gives, matrix by matrix, exactly what GivensAnnihilator gives.
+ */
+TEMPLATE_WITH_TYPE_T
+TEMPLATE_CONSTRAINT_REQUIRES_FPX
+class GivensBatchAnnihilator {
+private:
+    DTensor<T> *m_tensor;
+
+public:
+    GivensBatchAnnihilator() = delete;
+
+    GivensBatchAnnihilator(DTensor<T> &a) : m_tensor(&a) {}
+
+    void setTensor(DTensor<T> &a) { m_tensor = &a; }
+
+    /** In every matrix: left Givens rotation G(i, k) that zeroes element (k, j). */
+    void annihilate(size_t i, size_t k, size_t j) {
+        const size_t nR = m_tensor->numRows(), nC = m_tensor->numCols();
+        if (i >= nR or k >= nR or i == k) throw std::invalid_argument("[GivensBatchAnnihilator::annihilate] invalid row index");
+        if (j >= nC) throw std::invalid_argument("[GivensBatchAnnihilator::annihilate] invalid column index j");
+        gpuErrChk(gpub200::Abi<T>::annihilate_batched(gpub200::ctx(), (int) m_tensor->streamIdx(), m_tensor->raw(), nR, nC, nR * nC, i, k, j,
+                                                      m_tensor->numMats()));
+    }
+
+    /** In every matrix b: rows i and j rotated with (c[b], minus_s[b]), device arrays of numMats values (cuBLAS rot convention). */
+    void applyLeftGivensRotations(size_t i, size_t j, const T *c, const T *minus_s) {
+        const size_t nR = m_tensor->numRows(), nC = m_tensor->numCols();
+        if (i >= nR or j >= nR) throw std::invalid_argument("[GivensBatchAnnihilator] invalid row index");
+        gpuErrChk(gpub200::Abi<T>::rot_batched(gpub200::ctx(), (int) m_tensor->streamIdx(), nC, m_tensor->raw() + i, nR, m_tensor->raw() + j, nR,
+                                               nR * nC, c, minus_s, m_tensor->numMats()));
+    }
+
+    /** In every matrix b: columns i and j rotated with (c[b], minus_s[b]). */
+    void applyRightGivensRotations(size_t i, size_t j, const T *c, const T *minus_s) {
+        const size_t nR = m_tensor->numRows(), nC = m_tensor->numCols();
+        if (i >= nC or j >= nC) throw std::invalid_argument("[GivensBatchAnnihilator] invalid column index");
+        gpuErrChk(gpub200::Abi<T>::rot_batched(gpub200::ctx(), (int) m_tensor->streamIdx(), nR, m_tensor->raw() + i * nR, 1,
+                                               m_tensor->raw() + j * nR, 1, nR * nC, c, minus_s, m_tensor->numMats()));
+    }
+};
+
 /** Kept for source compatibility with the reference header (annihilate() uses gpub_givens_rhypot_*). */
 TEMPLATE_WITH_TYPE_T
 TEMPLATE_CONSTRAINT_REQUIRES_FPX

@@ -121,6 +121,19 @@ int gpub_rot_f32(gpub_ctx_t ctx, int sidx, size_t n, float *x, size_t incx, floa
 /* ref: tensor.cuh:2272-2281 (k_givensAnnihilateRHypot): res = {rhypot, cos, -sin} */
 int gpub_givens_rhypot_f64(gpub_ctx_t ctx, int sidx, const double *data, double *res, size_t i, size_t k, size_t j, size_t nrows);
 int gpub_givens_rhypot_f32(gpub_ctx_t ctx, int sidx, const float *data, float *res, size_t i, size_t k, size_t j, size_t nrows);
+/* Batched Givens (additive: the reference rotates one matrix per call and refuses tensors, tensor.cuh:1076, 1090, 2229).
+ * rot_batched: x_b <- c_b x_b + s_b y_b, y_b <- c_b y_b - s_b x_b for every matrix b (x, y given for matrix 0, `stride` elements
+ * between matrices), c and s DEVICE arrays of `batch` values.
+ * givens_annihilate_batched: for every matrix the left rotation G(i, k) that zeroes element (k, j), built from elements (i, j) and
+ * (k, j) exactly as k_givensAnnihilateRHypot (cos = x_ij rhypot, -sin = x_kj rhypot), applied to rows i and k: one launch.    */
+int gpub_rot_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, double *x, size_t incx, double *y, size_t incy, size_t stride,
+                         const double *c, const double *s, size_t batch);
+int gpub_rot_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, float *x, size_t incx, float *y, size_t incy, size_t stride,
+                         const float *c, const float *s, size_t batch);
+int gpub_givens_annihilate_batched_f64(gpub_ctx_t ctx, int sidx, double *A, size_t nrows, size_t ncols, size_t strideA,
+                                       size_t i, size_t k, size_t j, size_t batch);
+int gpub_givens_annihilate_batched_f32(gpub_ctx_t ctx, int sidx, float *A, size_t nrows, size_t ncols, size_t strideA,
+                                       size_t i, size_t k, size_t j, size_t batch);
 /* ref: tensor.cuh:1396-1424 (getRows: one strided copy per row) -> one launch:
  * dst(r, c) = src(row_from + r, c) for r < nrows_out, c < ncols             */
 int gpub_gather_rows_f64(gpub_ctx_t ctx, int sidx, const double *src, size_t ld_src, size_t row_from,

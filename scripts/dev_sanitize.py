@@ -28,5 +28,10 @@ for (m, n, k) in [(1024, 128, 2), (300, 40, 2), (513, 38, 1)]:
     capi.ormqr_batched(ctx, False, A, tau, Cq); capi.ormqr_batched(ctx, True, A, tau, Cq)
 S, U, Vt, info = capi.gesvd_batched(ctx, capi.from_numpy_batch(rng.uniform(-1, 1, (2, 256, 64))), True)
 S, U, Vt, info = capi.gesvd_batched(ctx, capi.from_numpy_batch(rng.uniform(-1, 1, (2, 200, 100)).astype(np.float32)), False)
+a = capi.from_numpy_batch(rng.uniform(-1, 1, (3, 64, 192)))                 # fat 64 x 192: Nullspace through the block-reflector U assembly
+N, P, rank = capi.nullspace_build(ctx, a)
+bb = capi.from_numpy_batch(rng.uniform(-1, 1, (3, 192, 1))); capi.nullspace_project(ctx, P, bb)
+G = capi.from_numpy_batch(rng.uniform(-1, 1, (70, 6, 5)))
+ctx.call("givens_annihilate_batched", G, capi._p(G), 6, 5, 30, 0, 5, 0, 70)
 torch.cuda.synchronize()
 print("done")

@@ -5,6 +5,7 @@
 // Built by __graft_entry__.build() into build/tests/additive_test; driven by tests/test_gpu_additive.py.
 #include <tensor.cuh>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <random>
@@ -267,8 +268,68 @@ static void nullspaceOnAnotherStream() {
     report("svd_refuses_unsupported_shapes_with_an_exception", threw);
 }
 
+// GivensBatchAnnihilator on a (m, n, k) tensor == GivensAnnihilator looped over the k matrices (what a reference user writes)
+template<typename T>
+static void givensBatchCase(size_t m, size_t n, size_t k, double tol, const char *tag) {
+    std::vector<T> a = uniform<T>(m * n * k, 51 + m);
+    DTensor<T> AB(a, m, n, k);
+    GivensBatchAnnihilator<T> gb(AB);
+    // reduce column 0, then column 1, to upper-triangular form like the reference's test (testTensor.cu givensAnnihilate...)
+    for (size_t j = 0; j < std::min<size_t>(n, 3); j++)
+        for (size_t r = m - 1; r > j; r--) gb.annihilate(j, r, j);
+    std::vector<T> outB;
+    AB.download(outB);
+    std::vector<T> outL(m * n * k);
+    for (size_t i = 0; i < k; i++) {
+        std::vector<T> ai(a.begin() + i * m * n, a.begin() + (i + 1) * m * n);
+        DTensor<T> A1(ai, m, n, 1);
+        GivensAnnihilator<T> g1(A1);
+        for (size_t j = 0; j < std::min<size_t>(n, 3); j++)
+            for (size_t r = m - 1; r > j; r--) g1.annihilate(j, r, j);
+        std::vector<T> t;
+        A1.download(t);
+        std::copy(t.begin(), t.end(), outL.begin() + i * m * n);
+    }
+    const double d = relDiff(outB, outL);
+    const bool exact = std::memcmp(outB.data(), outL.data(), outB.size() * sizeof(T)) == 0;
+    report((std::string("givens_batch_equals_loop_") + tag).c_str(), d <= tol, "rel=" + sci(d) + (exact ? " bit-identical" : ""));
+    double below = 0, na = 0, nb = 0;
+    for (size_t i = 0; i < k; i++)
+        for (size_t j = 0; j < n; j++)
+            for (size_t r = 0; r < m; r++) {
+                const double v = outB[i * m * n + r + j * m], w = a[i * m * n + r + j * m];
+                if (j < 3 && r > j) below = std::max(below, std::fabs(v));
+                nb += v * v; na += w * w;
+            }
+    report((std::string("givens_batch_zeroes_and_preserves_norm_") + tag).c_str(), below <= 50 * tol && std::fabs(std::sqrt(nb / na) - 1.0) <= 50 * tol,
+           "below=" + sci(below) + " norm_ratio-1=" + sci(std::sqrt(nb / na) - 1.0));
+    // per-matrix (c, s) rotations from device arrays
+    std::vector<T> cs(2 * k);
+    for (size_t i = 0; i < k; i++) { const double th = 0.1 * (double) (i + 1); cs[i] = (T) std::cos(th); cs[k + i] = (T) std::sin(th); }
+    DTensor<T> dcs(cs, 2 * k), X(a, m, n, k);
+    GivensBatchAnnihilator<T> gx(X);
+    gx.applyLeftGivensRotations(0, m - 1, dcs.raw(), dcs.raw() + k);
+    gx.applyRightGivensRotations(0, n - 1, dcs.raw(), dcs.raw() + k);
+    std::vector<T> got;
+    X.download(got);
+    std::vector<double> ref(a.begin(), a.end());
+    for (size_t i = 0; i < k; i++) {
+        const double c = cs[i], s_ = cs[k + i];
+        double *ai = ref.data() + i * m * n;
+        for (size_t j = 0; j < n; j++) { const double x = ai[0 + j * m], y = ai[m - 1 + j * m]; ai[0 + j * m] = c * x + s_ * y; ai[m - 1 + j * m] = c * y - s_ * x; }
+        for (size_t r = 0; r < m; r++) { const double x = ai[r], y = ai[r + (n - 1) * m]; ai[r] = c * x + s_ * y; ai[r + (n - 1) * m] = c * y - s_ * x; }
+    }
+    std::vector<T> refT(ref.begin(), ref.end());
+    report((std::string("rot_batched_matches_host_") + tag).c_str(), relDiff(got, refT) <= 10 * tol, "rel=" + sci(relDiff(got, refT)));
+    bool threw = false;
+    try { gb.annihilate(0, m, 0); } catch (const std::invalid_argument &) { threw = true; }
+    report((std::string("givens_batch_bad_index_throws_") + tag).c_str(), threw);
+}
+
 int main() {
     Session::setStreams(3);
+    givensBatchCase<double>(6, 5, 37, 1e-14, "f64_6x5x37");
+    givensBatchCase<float>(9, 4, 300, 2e-6, "f32_9x4x300");
     hostPipelineCase<double>(32, 5000, 7, false, "f64_32_pageable");
     hostPipelineCase<double>(32, 5000, 16, true, "f64_32_pinned");
     hostPipelineCase<float>(16, 3, 16, false, "f32_16_more_chunks_than_matrices");
