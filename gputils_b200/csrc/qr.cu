@@ -89,6 +89,7 @@ __device__ void householder_panel(T *M, size_t ld, int m, int n, int ncols, T *t
                 for (int r = j + 1 + lane; r < m; r += 32) w = fma(cj[r], cc[r], w);
                 w = warp_sum(w) + cc[j];
                 const T tw = tau * w;
+                __syncwarp();                               // every lane has read cc[j] before lane 0 overwrites it
                 if (lane == 0) cc[j] -= tw;
                 for (int r = j + 1 + lane; r < m; r += 32) cc[r] = fma(-tw, cj[r], cc[r]);
             }

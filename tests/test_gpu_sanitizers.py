@@ -24,9 +24,12 @@ SAN = "/usr/local/cuda/bin/compute-sanitizer"
 
 
 def _errors(out: str) -> int:
+    """errors (memcheck / synccheck: `ERROR SUMMARY: N errors`) plus, for racecheck, every hazard it displays, warnings included
+    (`RACECHECK SUMMARY: H hazards displayed (E errors, W warnings)`)"""
     m = re.findall(r"ERROR SUMMARY: (\d+) error", out)
-    assert m, out[-3000:]
-    return sum(int(x) for x in m)
+    h = re.findall(r"RACECHECK SUMMARY: (\d+) hazard", out)
+    assert m or h, out[-3000:]
+    return sum(int(x) for x in m) + sum(int(x) for x in h)
 
 
 def _run(args, timeout=1800):
