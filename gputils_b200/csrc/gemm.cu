@@ -343,9 +343,6 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(size_t m, size_t n, size_t k
 // = 2 x 4 DMMA tiles (m8n8k4). K panels of 16 staged with cp.async, double buffered.
 // Requires m, n multiples of 64 and k a multiple of 16 (the launcher checks).
 // ------------------------------------------------------------------------------------------
-#ifndef GPUB_DMMA_STAGES
-#define GPUB_DMMA_STAGES 3
-#endif
 constexpr int DK = 16;
 constexpr int DLD = 64 + 4; // leading dimension == 4 (mod 16) doubles: the 16 lanes of a half-warp hit 16 distinct bank pairs
 
@@ -372,10 +369,7 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // N N^T = U2 U2^T = I - U1 U1^T with U1 = U(:, 0:r): per matrix the kernel takes whichever side has FEWER columns (rank r read from
 // the device) -- A = N with k = n - r columns, or Ualt = U with k = r columns, alpha = -1 and the identity added in the epilogue.
 // For a fat 128 x 1024 matrix (r = 128) that is 128 instead of 896 columns: 7 x fewer flops for the same projector.
-// STAGES: depth of the cp.async ring. 2: load panel p + 1 while panel p is multiplied, two CTA barriers per panel. 3: panel p + 2 is
-// requested right after the barrier that publishes panel p (its buffer was last read in iteration p - 1, which every thread has left
-// by then), so one barrier per panel suffices and a panel has two iterations to arrive.
-template<bool TRB, int DKT, int WARPS = 8, bool SYM = false, bool PROJ = false, int STAGES = 2>
+template<bool TRB, int DKT, int WARPS = 8, bool SYM = false, bool PROJ = false>
 __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
@@ -385,7 +379,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
     constexpr int BROWS = TRB ? DKT : 64, BLD = TRB ? DLD : DKT + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double (*As)[DKT][DLD] = reinterpret_cast<double (*)[DKT][DLD]>(smem_raw);
-    double (*Bs)[BROWS][BLD] = reinterpret_cast<double (*)[BROWS][BLD]>(smem_raw + sizeof(double) * STAGES * DKT * DLD);
+    double (*Bs)[BROWS][BLD] = reinterpret_cast<double (*)[BROWS][BLD]>(smem_raw + sizeof(double) * 2 * DKT * DLD);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NTH = 32 * WARPS, WM = WARPS == 8 ? 16 : 32, MI = WM / 8, WR = 64 / WM;
     const int wr = (warp % WR) * WM, wc = (warp / WR) * 32; // warp origin inside the tile
@@ -447,7 +441,25 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
         };
 
         const size_t npan = PROJ ? (kcount + DKT - 1) / DKT : k / DKT;
-        auto multiply_panel = [&](int buf) {
+        if (npan > 0) load_panel(0, 0);
+        for (size_t p = 0; p < npan; p++) {
+            const int buf = (int) (p & 1);
+            if (p + 1 < npan) {
+                load_panel(buf ^ 1, (p + 1) * DKT);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            if (PROJ && comp && p + 1 == npan && kcount % DKT != 0) {
+                // the columns of U beyond the rank that came along with the last panel do not belong to U1
+                const int kv = (int) (kcount % DKT);
+                for (int e = threadIdx.x; e < (DKT - kv) * 64; e += NTH) {
+                    As[buf][kv + e / 64][e % 64] = 0.0;
+                    Bs[buf][kv + e / 64][e % 64] = 0.0;
+                }
+                __syncthreads();
+            }
 #pragma unroll
             for (int k4 = 0; k4 < DKT; k4 += 4) {
                 double af[MI], bf[4];
@@ -460,40 +472,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
 #pragma unroll
                     for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
-        };
-        if (STAGES == 3) {
-            if (npan > 0) load_panel(0, 0);
-            if (npan > 1) load_panel(1, DKT);
-            for (size_t p = 0; p < npan; p++) {
-                if (p + 1 < npan) cp_async_wait<1>(); else cp_async_wait<0>();
-                __syncthreads();
-                if (p + 2 < npan) load_panel((int) ((p + 2) % 3), (p + 2) * DKT);
-                multiply_panel((int) (p % 3));
-            }
-            __syncthreads();                               // the next tile's first loads reuse buffers 0 and 1
-        } else {
-            if (npan > 0) load_panel(0, 0);
-            for (size_t p = 0; p < npan; p++) {
-                const int buf = (int) (p & 1);
-                if (p + 1 < npan) {
-                    load_panel(buf ^ 1, (p + 1) * DKT);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                if (PROJ && comp && p + 1 == npan && kcount % DKT != 0) {
-                    // the columns of U beyond the rank that came along with the last panel do not belong to U1
-                    const int kv = (int) (kcount % DKT);
-                    for (int e = threadIdx.x; e < (DKT - kv) * 64; e += NTH) {
-                        As[buf][kv + e / 64][e % 64] = 0.0;
-                        Bs[buf][kv + e / 64][e % 64] = 0.0;
-                    }
-                    __syncthreads();
-                }
-                multiply_panel(buf);
-                __syncthreads();
-            }
+            __syncthreads();
         }
         double *c = C + b * sC;
 #pragma unroll
@@ -1088,7 +1067,9 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
         const bool ok = (m % 64 == 0) && (n % 64 == 0) && (k % DK == 0) && k >= DK && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         ((((uintptr_t) A) | ((uintptr_t) B)) % 16 == 0) && (sA % 2 == 0) && (sB % 2 == 0);
         if (ok) {
-            if (GPUB_DMMA_DKT32 && k % 32 == 0) {   // measured: 32-deep panels are 2 % slower than 16-deep ones on 128^3 (profiles/r1e)
+            // measured on 128^3: 32-deep panels are 2 % slower than 16-deep ones (profiles/r1e), and a 3-stage cp.async ring with one
+            // barrier per panel instead of two is 1 % slower than the 2-stage one (29.4 against 29.7 TFLOP/s, round 2)
+            if (GPUB_DMMA_DKT32 && k % 32 == 0) {
                 constexpr size_t smem32 = sizeof(double) * (2 * 32 * DLD + 2 * 64 * (32 + 4));
                 GPUB_CUDA(cudaFuncSetAttribute(k_gemm_dmma<false, 32, GPUB_DMMA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem32));
                 k_gemm_dmma<false, 32, GPUB_DMMA_WARPS><<<grid, 32 * GPUB_DMMA_WARPS, smem32, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
@@ -1096,15 +1077,8 @@ int gemm_batched(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, T alpha
             } else {
                 constexpr size_t smem16 = sizeof(double) * (2 * 16 * DLD + 2 * 64 * (16 + 4));
 #if GPUB_DMMA_WARPS == 4
-#if GPUB_DMMA_STAGES == 3
-                constexpr size_t smem3 = sizeof(double) * (3 * 16 * DLD + 3 * 64 * (16 + 4));
-                GPUB_CUDA(cudaFuncSetAttribute(k_gemm_dmma<false, 16, 4, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem3));
-                k_gemm_dmma<false, 16, 4, false, false, 3><<<grid, 128, smem3, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA,
-                                                                                        (const double *) B, ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
-#else
                 k_gemm_dmma<false, 16, 4><<<grid, 128, smem16, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
                                                                          ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
-#endif
 #else
                 k_gemm_dmma<false, 16><<<grid, 256, smem16, stream>>>(m, n, k, (double) alpha, (const double *) A, lda, sA, (const double *) B,
                                                                       ldb, sB, (double) beta, (double *) C, ldc, sC, tm, tn, batch);
