@@ -898,6 +898,14 @@ def run_sharded_api(n_devices: int):
                     res["allgather_GBps"][transport] = float(ln.rsplit("GBps_into_each_device=", 1)[1].split()[0])
                 except (IndexError, ValueError):
                     pass
+            if ln.startswith("INFO solve_allgather"):
+                # potrs followed by an all-gather of x, against the solve kernel that stores x into every device's tensor itself
+                try:
+                    kv = dict(t.split("=") for t in ln.split()[2:])
+                    res.setdefault("solve_allgather_ms", {})[transport] = {"separate": float(kv["separate_ms"]), "fused_kernel": float(kv["fused_ms"]),
+                                                                           "systems": int(kv["systems"])}
+                except (KeyError, ValueError):
+                    pass
         if not ok:
             res[transport + "_tail"] = out[-800:]
     return res

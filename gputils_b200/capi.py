@@ -43,6 +43,7 @@ _TYPED = {
     "gemm_batched": [_sz, _sz, _sz, "T", _vp, _sz, _sz, _vp, _sz, _sz, "T", _vp, _sz, _sz, _sz],
     "potrf_batched": [_sz, _vp, _sz, _sz, _vp, _sz],
     "potrs_batched": [_sz, _vp, _sz, _sz, _vp, _sz, _sz],
+    "potrs_allgather_batched": [_sz, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _int, _sz, _sz],
     "geqrf_batched": [_sz, _sz, _vp, _sz, _sz, _vp, _sz, _sz],
     "ormqr_batched": [_int, _sz, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _sz, _sz],
     "trsv_upper_batched": [_sz, _vp, _sz, _sz, _vp, _sz, _sz],

@@ -681,9 +681,19 @@ __global__ void __launch_bounds__(256) k_potrf_cta(int n, T *A, size_t lda, size
 #define GPUB_POTRS_MINB 5
 #endif
 
-template<typename T, int NP, bool DENSE>
+// Fused solve + all-gather (GATHER): every solution is also stored straight into the gathered tensor of up to 8 devices
+// (peers.x[p] + (peers.offset + matrix) * peers.stride, NVLink peer stores from inside the kernel), so the all-gather that would
+// follow the solve of a sharded batch costs no second pass and no second launch.
+template<typename T>
+struct PotrsPeers {
+    T *x[8];
+    int count;
+    size_t offset, stride;
+};
+
+template<typename T, int NP, bool DENSE, bool GATHER = false>
 __global__ void __launch_bounds__(GPUB_POTRS_THREADS, GPUB_POTRS_MINB)
-k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b, size_t strideB, size_t batch) {
+k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b, size_t strideB, size_t batch, PotrsPeers<T> peers) {
     constexpr int GROUPS = GPUB_POTRS_THREADS / NP;
     constexpr int LDP = NP + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -731,7 +741,14 @@ k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *
             x = fma(-l[jj], vj, x);
         }
         x *= dinv;
-        if (row_ok && live) b_g[i] = x;
+        if (row_ok && live) {
+            b_g[i] = x;
+            if (GATHER) {
+#pragma unroll
+                for (int pr = 0; pr < 8; pr++)
+                    if (pr < peers.count) peers.x[pr][(peers.offset + mat) * peers.stride + i] = x;
+            }
+        }
     }
 }
 
@@ -1085,18 +1102,28 @@ int potrf_batched(gpub_ctx_t ctx, int sidx, size_t n, T *A, size_t lda, size_t s
 }
 
 template<typename T>
-int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, size_t strideL, T *b, size_t strideB, size_t batch) {
+int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, size_t strideL, T *b, size_t strideB, size_t batch,
+                  const PotrsPeers<T> *peers = nullptr) {
     if (n == 0 || batch == 0) return GPUB_OK;
     if (!L || !b || ldl < n) return GPUB_EINVAL;
     if (n > 8192) return GPUB_ENOTSUP;
     GPUB_ENTER(ctx, sidx);
-    if (GPUB_CHOL4 && n == 4 && ldl == 4 && strideL == 16 && strideB == 4 && ((((uintptr_t) L) | ((uintptr_t) b)) & 15u) == 0) {
+    if (peers && n > 32) {
+        // shapes without a fused kernel: plain solve, then one peer copy of the shard per destination (same stream)
+        int e = potrs_batched<T>(ctx, sidx, n, L, ldl, strideL, b, strideB, batch, nullptr);
+        if (e) return e;
+        for (int p = 0; p < peers->count; p++)
+            GPUB_CUDA(cudaMemcpy2DAsync(peers->x[p] + peers->offset * peers->stride, peers->stride * sizeof(T), b, strideB * sizeof(T), n * sizeof(T),
+                                        batch, cudaMemcpyDefault, stream));
+        return GPUB_OK;
+    }
+    if (!peers && GPUB_CHOL4 && n == 4 && ldl == 4 && strideL == 16 && strideB == 4 && ((((uintptr_t) L) | ((uintptr_t) b)) & 15u) == 0) {
         const size_t want = gpub_ceil_div(batch, (size_t) 128), cap = (size_t) ctx->sm_count * 16;
         k_potrs4<T><<<(unsigned) (want < cap ? want : cap), 128, 0, stream>>>(L, b, batch);
         GPUB_LAUNCH_CHECK();
         return GPUB_OK;
     }
-    if (GPUB_CHOL4 && sizeof(T) == 4 && n == 8 && ldl == 8 && strideL == 64 && strideB == 8 && ((((uintptr_t) L) | ((uintptr_t) b)) & 15u) == 0) {
+    if (!peers && GPUB_CHOL4 && sizeof(T) == 4 && n == 8 && ldl == 8 && strideL == 64 && strideB == 8 && ((((uintptr_t) L) | ((uintptr_t) b)) & 15u) == 0) {
         const size_t want = gpub_ceil_div(batch, (size_t) 128), cap = (size_t) ctx->sm_count * 16;
         k_potrs8_f32<<<(unsigned) (want < cap ? want : cap), 128, 0, stream>>>((const float *) L, (float *) b, batch);
         GPUB_LAUNCH_CHECK();
@@ -1112,9 +1139,15 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
         const bool dense = (n == (size_t) np) && ldl == n;
 #define GPUB_POTRS_LAUNCH(NPV, DN)                                                                                   \
     {                                                                                                                \
-        auto kern = k_potrs_group<T, NPV, DN>;                                                                       \
-        if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-        kern<<<grid, GPUB_POTRS_THREADS, smem, stream>>>((int) n, L, ldl, strideL, b, strideB, batch);               \
+        if (peers) {                                                                                                 \
+            auto kern = k_potrs_group<T, NPV, DN, true>;                                                             \
+            if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+            kern<<<grid, GPUB_POTRS_THREADS, smem, stream>>>((int) n, L, ldl, strideL, b, strideB, batch, *peers);   \
+        } else {                                                                                                     \
+            auto kern = k_potrs_group<T, NPV, DN, false>;                                                            \
+            if (smem > 48 * 1024) GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+            kern<<<grid, GPUB_POTRS_THREADS, smem, stream>>>((int) n, L, ldl, strideL, b, strideB, batch, PotrsPeers<T>()); \
+        }                                                                                                            \
     }
 #define GPUB_POTRS_CASE(NPV)                                                                                         \
     if (dense) GPUB_POTRS_LAUNCH(NPV, true) else GPUB_POTRS_LAUNCH(NPV, false)
@@ -1156,5 +1189,18 @@ int gpub_potrf_batched_f64(gpub_ctx_t c, int s, size_t n, double *A, size_t lda,
 int gpub_potrf_batched_f32(gpub_ctx_t c, int s, size_t n, float *A, size_t lda, size_t sA, int *info, size_t b) { return potrf_batched<float>(c, s, n, A, lda, sA, info, b); }
 int gpub_potrs_batched_f64(gpub_ctx_t c, int s, size_t n, const double *L, size_t ldl, size_t sL, double *b, size_t sB, size_t bt) { return potrs_batched<double>(c, s, n, L, ldl, sL, b, sB, bt); }
 int gpub_potrs_batched_f32(gpub_ctx_t c, int s, size_t n, const float *L, size_t ldl, size_t sL, float *b, size_t sB, size_t bt) { return potrs_batched<float>(c, s, n, L, ldl, sL, b, sB, bt); }
+
+#define GPUB_DEF_POTRS_GATHER(SUF, T)                                                                                 \
+    int gpub_potrs_allgather_batched_##SUF(gpub_ctx_t c, int s, size_t n, const T *L, size_t ldl, size_t sL, T *b, size_t sB, size_t bt, \
+                                           T *const *peer_x, int n_peers, size_t shard_offset, size_t stride_x) {     \
+        if (n_peers < 0 || n_peers > 8 || (n_peers && !peer_x) || stride_x < n) return GPUB_EINVAL;                   \
+        PotrsPeers<T> pp;                                                                                             \
+        for (int p = 0; p < 8; p++) pp.x[p] = p < n_peers ? peer_x[p] : nullptr;                                      \
+        for (int p = 0; p < n_peers; p++) if (!pp.x[p]) return GPUB_EINVAL;                                           \
+        pp.count = n_peers; pp.offset = shard_offset; pp.stride = stride_x;                                           \
+        return potrs_batched<T>(c, s, n, L, ldl, sL, b, sB, bt, n_peers ? &pp : nullptr);                             \
+    }
+GPUB_DEF_POTRS_GATHER(f64, double)
+GPUB_DEF_POTRS_GATHER(f32, float)
 
 } // extern "C"

@@ -301,6 +301,7 @@ template<typename T> struct Abi;
         static constexpr auto gemm = gpub_gemm_batched_##SUF;                                                       \
         static constexpr auto potrf = gpub_potrf_batched_##SUF;                                                     \
         static constexpr auto potrs = gpub_potrs_batched_##SUF;                                                     \
+        static constexpr auto potrs_allgather = gpub_potrs_allgather_batched_##SUF;                                 \
         static constexpr auto geqrf = gpub_geqrf_batched_##SUF;                                                     \
         static constexpr auto ormqr = gpub_ormqr_batched_##SUF;                                                     \
         static constexpr auto trsv = gpub_trsv_upper_batched_##SUF;                                                 \

@@ -291,11 +291,12 @@ class ShardedCholeskyBatchFactoriser {
 private:
     ShardedDTensor<T> *m_matrix;
     std::vector<std::unique_ptr<CholeskyBatchFactoriser<T> > > m_factorisers;
+    bool m_factorisationDone = false;
 
 public:
     ShardedCholeskyBatchFactoriser() = delete;
 
-    ShardedCholeskyBatchFactoriser(ShardedDTensor<T> &A, bool factorised = false) : m_matrix(&A) {
+    ShardedCholeskyBatchFactoriser(ShardedDTensor<T> &A, bool factorised = false) : m_matrix(&A), m_factorisationDone(factorised) {
         if (A.numRows() != A.numCols()) throw std::invalid_argument("[CholeskyBatch] A must be square");
         m_factorisers.resize(A.numShards());
         A.forEachShard([&](size_t g, DTensor<T> &s) { m_factorisers[g] = std::make_unique<CholeskyBatchFactoriser<T> >(s, factorised); });
@@ -303,11 +304,45 @@ public:
 
     void factorise() {
         m_matrix->forEachShard([&](size_t g, DTensor<T> &) { m_factorisers[g]->factorise(); });
+        m_factorisationDone = true;
     }
 
     void solve(ShardedDTensor<T> &b) {
         m_matrix->checkSameSharding(b, "CholeskyBatchSolve");
         m_matrix->forEachShard([&](size_t g, DTensor<T> &) { m_factorisers[g]->solve(b.shard(g)); });
+    }
+
+    /**
+     * solve() and the all-gather of the solutions in ONE kernel per device: every device solves its shard and stores each
+     * solution straight into the gathered (n, 1, k) tensor of every device over NVLink (peer stores from inside the solve
+     * kernel, gpub_potrs_allgather_batched), so the gather costs no second pass over x and no NCCL launch. `b` is updated in
+     * place as by solve(). Returns the gathered solutions, result[g] living on device(g); blocks until they are complete.
+     */
+    std::vector<std::unique_ptr<DTensor<T> > > solveAllGather(ShardedDTensor<T> &b) {
+        if (!m_factorisationDone) throw std::logic_error("[CholeskyBatchSolve] no factor to solve with");
+        m_matrix->checkSameSharding(b, "CholeskyBatchSolve");
+        if (b.numCols() != 1 || b.numRows() != m_matrix->numRows()) throw std::invalid_argument("[CholeskyBatchSolve] A and b incompatible");
+        const size_t G = m_matrix->numShards(), n = m_matrix->numRows(), k = m_matrix->numMats();
+        if (G > 8) throw std::invalid_argument("[solveAllGather] at most 8 devices");
+        std::vector<std::unique_ptr<DTensor<T> > > full(G);
+        std::vector<T *> peers(G);
+        for (size_t g = 0; g < G; g++) {
+            gpub200::DeviceScope scope(m_matrix->device(g));
+            full[g] = std::make_unique<DTensor<T> >(n, 1, k);
+            peers[g] = full[g]->raw();
+        }
+        /* the result tensors were allocated on the legacy stream of their devices: they exist before any peer writes to them */
+        for (size_t g = 0; g < G; g++) {
+            gpub200::DeviceScope scope(m_matrix->device(g));
+            gpuErrChk(cudaStreamSynchronize(cudaStreamLegacy));
+        }
+        m_matrix->forEachShard([&](size_t g, DTensor<T> &s) {
+            DTensor<T> &bs = b.shard(g);
+            gpuErrChk(gpub200::Abi<T>::potrs_allgather(gpub200::ctx(), (int) s.streamIdx(), n, s.raw(), n, n * n, bs.raw(), n, s.numMats(),
+                                                       peers.data(), (int) G, m_matrix->shardRange(g).first, n));
+        });
+        m_matrix->synchronize();
+        return full;
     }
 
     /** Status codes of shard g ((1, 1, shard size)-tensor on device(g)). */

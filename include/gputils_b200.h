@@ -175,6 +175,17 @@ int gpub_potrs_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *L, 
 int gpub_potrs_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *L, size_t ldl, size_t strideL,
                            float *b, size_t strideB, size_t batch);
 
+/* Fused solve + all-gather over NVLink peer memory (additive; the gather of SURVEY 8(e) folded into the solve): potrs_batched on
+ * this device's shard of `batch` systems, and every solution x_i is ALSO stored, from inside the kernel, at
+ * peer_x[p] + (shard_offset + i) * stride_x for p < n_peers (<= 8) -- straight into the gathered (n, 1, k_total) tensor of every
+ * device, which must be mapped in this device's address space (gpub_multi_enable_peer_access). No second pass, no second launch.
+ * n <= 32 runs the fused kernel; larger n solve first and push the shard with one peer copy per destination on the same stream. */
+int gpub_potrs_allgather_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *L, size_t ldl, size_t strideL,
+                                     double *b, size_t strideB, size_t batch, double *const *peer_x, int n_peers,
+                                     size_t shard_offset, size_t stride_x);
+int gpub_potrs_allgather_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *L, size_t ldl, size_t strideL,
+                                     float *b, size_t strideB, size_t batch, float *const *peer_x, int n_peers,
+                                     size_t shard_offset, size_t stride_x);
 /* Host pipeline (additive; the reference has whole-tensor upload -> factorise -> solve -> download, tensor.cuh:1128-1154,
  * 2135-2197): the dense batch A_host (n*n per matrix) / b_host (n per matrix) is cut into `chunks` pieces (0 = default 16);
  * each piece is uploaded into A_dev / b_dev, factorised and solved as soon as it has landed, and x / info are downloaded behind

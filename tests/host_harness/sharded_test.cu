@@ -103,6 +103,29 @@ int main(int argc, char **argv) {
             ok = same(got, L1);
         }
         report("allgather_ragged_every_device_holds_the_batch", ok, std::string("transport=") + (used == GPUB_GATHER_NCCL ? "nccl" : "p2p"));
+
+        // solve + all-gather fused into the solve kernel (peer stores over NVLink): same bits on every device, and in b itself
+        if (G <= 8) {
+            ShardedDTensor<double> bF(b, n, 1, k, devices);
+            auto xs = fS.solveAllGather(bF);
+            bool okf = xs.size() == G;
+            for (size_t g = 0; g < G && okf; g++) {
+                gpub200::DeviceScope scope(devices[g]);
+                std::vector<double> got;
+                xs[g]->download(got);
+                okf = same(got, x1);
+            }
+            std::vector<double> xF;
+            bF.download(xF);
+            report("fused_solve_allgather_bit_identical_on_every_device", okf && same(xF, x1));
+            bool threw = false;
+            try {
+                ShardedDTensor<double> A3(a, n, n, k, devices);
+                ShardedCholeskyBatchFactoriser<double> f3(A3);
+                f3.solveAllGather(bF);
+            } catch (const std::logic_error &) { threw = true; }
+            report("fused_solve_allgather_needs_a_factor", threw);
+        }
     }
 
     {   // ---- addAB, 8 x 8 fp64, k = 4096 (BASELINE config 1), operators, reductions ----
@@ -203,6 +226,29 @@ int main(int argc, char **argv) {
         const double bytesIn = (double) (n * n * k * sizeof(double)) * (double) (G - 1) / (double) G;   // received per device
         std::printf("INFO allgather transport=%s shards=%zu bytes_per_device=%.0f seconds=%.6f (includes allocating the %zu result tensors) "
                     "GBps_into_each_device=%.1f\n", used == GPUB_GATHER_NCCL ? "nccl" : "p2p", G, bytesIn, sec, G, bytesIn / sec / 1e9);
+    }
+
+    if (G <= 8) {   // ---- fused solve + all-gather against solve followed by all-gather of x (reported, not asserted) ----
+        const size_t n = 32, k = gatherMats - gatherMats % G;
+        std::vector<double> a1 = spd(n, 1, 7);
+        std::vector<double> a(n * n * k), b = uniform<double>(n * k, 8);
+        for (size_t i = 0; i < k; i++) std::copy(a1.begin(), a1.end(), a.begin() + i * n * n);
+        ShardedDTensor<double> AS(a, n, n, k, devices), bS(b, n, 1, k, devices), bF(b, n, 1, k, devices);
+        ShardedCholeskyBatchFactoriser<double> fS(AS);
+        fS.factorise();
+        { auto w1 = fS.solveAllGather(bF); fS.solve(bS); auto w2 = bS.allGather(transport); }   // warm-up (pool, NCCL clique)
+        bS.upload(b); bF.upload(b);
+        AS.synchronize();
+        auto t0 = std::chrono::steady_clock::now();
+        fS.solve(bS);
+        auto sep = bS.allGather(transport);
+        auto t1 = std::chrono::steady_clock::now();
+        auto fused = fS.solveAllGather(bF);
+        auto t2 = std::chrono::steady_clock::now();
+        const double tsep = std::chrono::duration<double>(t1 - t0).count(), tfus = std::chrono::duration<double>(t2 - t1).count();
+        const double bytesIn = (double) (n * k * sizeof(double)) * (double) (G - 1) / (double) G;
+        std::printf("INFO solve_allgather systems=%zu shards=%zu separate_ms=%.3f fused_ms=%.3f x_bytes_into_each_device=%.0f\n", k, G, tsep * 1e3,
+                    tfus * 1e3, bytesIn);
     }
 
     std::printf("%s failures=%d\n", g_fail ? "FAILED" : "ALL PASSED", g_fail);
