@@ -54,7 +54,7 @@ __device__ __forceinline__ double block_sum(double v) {
 
 template<typename T, int OP, bool VEC>
 __global__ void __launch_bounds__(kThreads) k_reduce_sum(size_t n, const T *__restrict__ x, const T *__restrict__ y,
-                                                         double *partials, unsigned int *ticket, T *out, bool take_sqrt) {
+                                                         double *partials, unsigned int *ticket, T *out, bool take_sqrt, double prescale) {
     using V = typename VecOf<T>::type;
     constexpr int VN = VecOf<T>::N;
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,12 +71,12 @@ __global__ void __launch_bounds__(kThreads) k_reduce_sum(size_t n, const T *__re
             unpack<T>(xv[i], a);
             if (OP == OP_DOT) unpack<T>(yv[i], b);
 #pragma unroll
-            for (int j = 0; j < VN; j++) acc += term<OP>((double) a[j], OP == OP_DOT ? (double) b[j] : 0.0);
+            for (int j = 0; j < VN; j++) acc += term<OP>((double) a[j] * prescale, OP == OP_DOT ? (double) b[j] : 0.0);
         }
         done = nv * VN;
     }
     for (size_t i = done + tid; i < n; i += nth)
-        acc += term<OP>((double) x[i], OP == OP_DOT ? (double) y[i] : 0.0);
+        acc += term<OP>((double) x[i] * prescale, OP == OP_DOT ? (double) y[i] : 0.0);
 
     double bs = block_sum(acc);
     __shared__ bool s_last;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_sum(size_t n, const T *__re
 }
 
 template<typename T, int OP>
-int reduce_sum(gpub_ctx_t ctx, int sidx, size_t n, const T *x, const T *y, T *result_host, bool take_sqrt) {
+int reduce_sum(gpub_ctx_t ctx, int sidx, size_t n, const T *x, const T *y, T *result_host, bool take_sqrt, double prescale = 1.0) {
     if (!result_host) return GPUB_EINVAL;
     if (n == 0) {
         *result_host = T(0);
@@ -114,9 +114,9 @@ int reduce_sum(gpub_ctx_t ctx, int sidx, size_t n, const T *x, const T *y, T *re
     T *out = reinterpret_cast<T *>(slot->h_result);
     double *partials = reinterpret_cast<double *>(slot->d_scratch);
     if (vec)
-        k_reduce_sum<T, OP, true><<<grid, kThreads, 0, stream>>>(n, x, y, partials, slot->d_counter, out, take_sqrt);
+        k_reduce_sum<T, OP, true><<<grid, kThreads, 0, stream>>>(n, x, y, partials, slot->d_counter, out, take_sqrt, prescale);
     else
-        k_reduce_sum<T, OP, false><<<grid, kThreads, 0, stream>>>(n, x, y, partials, slot->d_counter, out, take_sqrt);
+        k_reduce_sum<T, OP, false><<<grid, kThreads, 0, stream>>>(n, x, y, partials, slot->d_counter, out, take_sqrt, prescale);
     GPUB_LAUNCH_CHECK();
     GPUB_CUDA(cudaStreamSynchronize(stream));
     *result_host = *out;
@@ -491,7 +491,25 @@ extern "C" {
 
 int gpub_dot_f64(gpub_ctx_t c, int s, size_t n, const double *x, const double *y, double *r) { return reduce_sum<double, OP_DOT>(c, s, n, x, y, r, false); }
 int gpub_dot_f32(gpub_ctx_t c, int s, size_t n, const float *x, const float *y, float *r) { return reduce_sum<float, OP_DOT>(c, s, n, x, y, r, false); }
-int gpub_nrm2_f64(gpub_ctx_t c, int s, size_t n, const double *x, double *r) { return reduce_sum<double, OP_SUMSQ>(c, s, n, x, nullptr, r, true); }
+// nrm2, fp64: the squares are summed unscaled (one pass at HBM speed); only when that sum overflowed or underflowed -- |x| beyond
+// ~1e154 or below ~1e-154, where cublasDnrm2's scaled algorithm still returns a finite value -- a second pass sums (x / max|x|)^2.
+// fp32 data cannot leave the range of the fp64 accumulator.
+int gpub_nrm2_f64(gpub_ctx_t c, int s, size_t n, const double *x, double *r) {
+    int e = reduce_sum<double, OP_SUMSQ>(c, s, n, x, nullptr, r, true);
+    if (e != GPUB_OK || n == 0) return e;
+    if (*r > 1e-140 && *r < 1e140) return GPUB_OK;      // sums of squares in [1e-280, 1e280] are exact enough: no second pass
+    double amax = 0.0;
+    e = reduce_abs<double, true>(c, s, n, x, &amax, nullptr);
+    if (e != GPUB_OK) return e;
+    if (!(amax > 0.0) || !(amax < 1.7976931348623157e308)) {   // all zero, or inf / NaN in the data: the plain result stands
+        if (amax == 0.0) *r = 0.0;
+        return GPUB_OK;
+    }
+    double scaled = 0.0;
+    e = reduce_sum<double, OP_SUMSQ>(c, s, n, x, nullptr, &scaled, true, 1.0 / amax);
+    if (e == GPUB_OK) *r = amax * scaled;
+    return e;
+}
 int gpub_nrm2_f32(gpub_ctx_t c, int s, size_t n, const float *x, float *r) { return reduce_sum<float, OP_SUMSQ>(c, s, n, x, nullptr, r, true); }
 int gpub_asum_f64(gpub_ctx_t c, int s, size_t n, const double *x, double *r) { return reduce_sum<double, OP_ASUM>(c, s, n, x, nullptr, r, false); }
 int gpub_asum_f32(gpub_ctx_t c, int s, size_t n, const float *x, float *r) { return reduce_sum<float, OP_ASUM>(c, s, n, x, nullptr, r, false); }

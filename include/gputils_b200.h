@@ -98,6 +98,8 @@ int gpub_fill_ptr_table(gpub_ctx_t ctx, int sidx, void *base, size_t stride_byte
  * ref: tensor.cuh:968-1072 (dot, nrm2, asum, iamax, iamin)                   */
 int gpub_dot_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *x, const double *y, double *result_host);
 int gpub_dot_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *x, const float *y, float *result_host);
+/* nrm2: one pass, squares accumulated in fp64; if that sum over- or underflows (fp64 data beyond ~1e154 / below ~1e-154) a second,
+ * scaled pass returns what cublasDnrm2's scaled algorithm returns */
 int gpub_nrm2_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *x, double *result_host);
 int gpub_nrm2_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *x, float *result_host);
 int gpub_asum_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *x, double *result_host);

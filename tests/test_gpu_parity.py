@@ -380,3 +380,128 @@ def test_nullspace_projector_from_the_orthogonal_factor(gpu_ctx, dt, n):
     assert np.abs(P - N @ N.transpose(0, 2, 1)).max() <= tol and np.abs(P - P2).max() <= tol
     assert np.array_equal(P, P.transpose(0, 2, 1))
     assert np.abs(P[0] - np.eye(n)).max() <= tol and np.abs(P[7]).max() <= tol     # rank 0: identity; full rank: zero
+
+
+def test_nrm2_of_extreme_range_data_is_rescued_by_the_scaled_pass(gpu_ctx):
+    """fp64 data whose squares overflow / underflow: the one-pass sum gives inf / 0, the scaled second pass the true norm."""
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(3)
+    base = rng.uniform(0.5, 1.0, 100_003)
+    for scale in (1e200, 1e-200, 1e160, 1e-170, 1.0):
+        x = torch.from_numpy(base * scale).cuda()
+        got = capi.reduce_scalar(gpu_ctx, "nrm2", x)
+        want = float(np.linalg.norm(base)) * scale
+        assert np.isfinite(got) and abs(got / want - 1) <= 1e-13, (scale, got, want)
+    z = torch.zeros(1000, dtype=torch.float64, device="cuda")
+    assert capi.reduce_scalar(gpu_ctx, "nrm2", z) == 0.0
+    z[17] = float("inf")
+    assert capi.reduce_scalar(gpu_ctx, "nrm2", z) == float("inf")
+
+
+def test_pool_and_staged_copies_through_the_c_abi(gpu_ctx):
+    """gpub_mem_alloc / free / stats and gpub_upload / gpub_download (pageable numpy memory, odd sizes, > 4 ring pieces)."""
+    import ctypes as C
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    from gputils_b200 import capi
+    rng = np.random.default_rng(11)
+    for nbytes in (7, 300_001, (40 << 20) + 12345):
+        src = rng.integers(0, 255, nbytes, dtype=np.uint8)
+        dst = np.zeros_like(src)
+        p = C.c_void_p()
+        capi.check(lib.gpub_mem_alloc(h, nbytes, C.byref(p)), "gpub_mem_alloc")
+        capi.check(lib.gpub_upload(h, 0, p, src.ctypes.data_as(C.c_void_p), nbytes), "gpub_upload")
+        capi.check(lib.gpub_download(h, 0, dst.ctypes.data_as(C.c_void_p), p, nbytes), "gpub_download")
+        assert np.array_equal(src, dst)
+        reserved, used = C.c_size_t(), C.c_size_t()
+        capi.check(lib.gpub_mem_stats(h, C.byref(reserved), C.byref(used)), "gpub_mem_stats")
+        assert used.value >= nbytes and reserved.value >= used.value
+        capi.check(lib.gpub_mem_free(p), "gpub_mem_free")
+    assert lib.gpub_mem_free(C.c_void_p(12345)) != 0           # not a pool pointer: refused, not crashed
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,batch,pinned", [(32, 3001, True), (32, 3001, False), (16, 5, False), (64, 257, True)])
+def test_host_pipeline_equals_potrf_potrs(gpu_ctx, oracle, dt, n, batch, pinned):
+    """gpub_chol_solve_from_host_*: upload / factorise + solve / download of 7 chunks on three streams == the two plain launchers,
+    bit for bit, from pinned and from pageable host memory; info reported for a matrix that is not positive definite."""
+    import torch
+    from gputils_b200 import capi
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    A = oracle.fill_spd_batched(n, batch, float(n), 21, dt); b = oracle.fill_uniform(batch * n, -1.0, 1.0, 22, dt).reshape(batch, n, 1)
+    A[batch // 2, 0, 0] = -1.0
+    dA = dev(A); db = dev(b); info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    capi.potrf_batched(gpu_ctx, dA, info); capi.potrs_batched(gpu_ctx, dA, db)
+    hA = torch.from_numpy(np.ascontiguousarray(A.transpose(0, 2, 1))); hb = torch.from_numpy(np.ascontiguousarray(b.transpose(0, 2, 1)))
+    hx = torch.empty_like(hb); hi = torch.empty(batch, dtype=torch.int32)
+    if pinned:
+        hA, hb, hx, hi = hA.pin_memory(), hb.pin_memory(), hx.pin_memory(), hi.pin_memory()
+    dA2 = torch.empty((batch, n, n), dtype=tdt, device="cuda"); db2 = torch.empty((batch, 1, n), dtype=tdt, device="cuda")
+    info2 = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    capi.chol_solve_from_host(gpu_ctx, dA2, db2, info2, hA, hb, hx, hi, chunks=7)
+    ok = (info.cpu() == 0)
+    assert torch.equal(info.cpu(), info2.cpu()) and torch.equal(info2.cpu(), hi) and int(hi[batch // 2]) == 1
+    low = torch.triu(torch.ones(n, n)).bool()
+    assert torch.equal(dA.cpu()[ok][:, low], dA2.cpu()[ok][:, low])
+    assert torch.equal(db.cpu()[ok], db2.cpu()[ok]) and torch.equal(db2.cpu()[ok], hx[ok])
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n,batch", [(32, 1000), (8, 77), (20, 33), (64, 40)])
+def test_fused_solve_allgather_on_one_device(gpu_ctx, oracle, dt, n, batch):
+    """gpub_potrs_allgather_batched_*: the solutions also land at (offset + i) * stride of every destination (here three buffers on
+    the same device; two GPUs: tests/test_gpu_sharded.py), b itself is solved in place, nothing else is touched."""
+    import ctypes as C
+    import torch
+    from gputils_b200 import capi
+    A = oracle.fill_spd_batched(n, batch, float(n), 31, dt); b = oracle.fill_uniform(batch * n, -1.0, 1.0, 32, dt).reshape(batch, n, 1)
+    dA = dev(A); info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    capi.potrf_batched(gpu_ctx, dA, info)
+    x_ref = dev(b); capi.potrs_batched(gpu_ctx, dA, x_ref)
+    db = dev(b)
+    offset, stride, total = 5, n + 2, batch + 9
+    outs = [torch.full((total, stride), -7.0, dtype=db.dtype, device="cuda") for _ in range(3)]
+    ptrs = (C.c_void_p * 3)(*[o.data_ptr() for o in outs])
+    gpu_ctx.call("potrs_allgather_batched", db, n, capi._p(dA), n, n * n, capi._p(db), n, batch, ptrs, 3, offset, stride)
+    # fp32 8 x 8 has a thread-per-matrix solve of its own: same solution up to rounding; every other shape runs the same kernel
+    if n == 8 and dt == np.float32:
+        assert rel_err(db.cpu().numpy(), x_ref.cpu().numpy()) <= 10 * TOL[np.dtype(dt)]
+    else:
+        assert torch.equal(db, x_ref)
+    for o in outs:
+        assert torch.equal(o[offset:offset + batch, :n], db[:, 0, :])
+        assert bool((o[:offset] == -7.0).all()) and bool((o[offset + batch:] == -7.0).all()) and bool((o[:, n:] == -7.0).all())
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_batched_givens_through_the_c_abi(gpu_ctx, dt):
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(9)
+    m, n, batch = 7, 5, 129
+    A = rng.uniform(-1, 1, (batch, m, n)).astype(dt)
+    dA = dev(A)
+    gpu_ctx.call("givens_annihilate_batched", dA, capi._p(dA), m, n, m * n, 1, 4, 2, batch)
+    got = host(dA).astype(np.float64)
+    ref = A.astype(np.float64).copy()
+    h = 1.0 / np.hypot(ref[:, 1, 2], ref[:, 4, 2]); c = ref[:, 1, 2] * h; s = ref[:, 4, 2] * h
+    r1, r4 = ref[:, 1, :].copy(), ref[:, 4, :].copy()
+    ref[:, 1, :] = c[:, None] * r1 + s[:, None] * r4
+    ref[:, 4, :] = c[:, None] * r4 - s[:, None] * r1
+    tol = 10 * TOL[np.dtype(dt)]
+    assert np.abs(got - ref).max() <= tol and np.abs(got[:, 4, 2]).max() <= tol
+    cs = torch.from_numpy(np.stack([np.cos(np.arange(batch) * 0.1), np.sin(np.arange(batch) * 0.1)]).astype(dt)).cuda()
+    dB = dev(A)
+    # columns 0 and 3 of every matrix: x = column 0 (stride 1), y = column 3
+    gpu_ctx.call("rot_batched", dB, m, capi._p(dB), 1, C_void(dB, 3 * m), 1, m * n, capi._p(cs[0]), capi._p(cs[1]), batch)
+    gb = host(dB).astype(np.float64); rb = A.astype(np.float64).copy()
+    cc, ss = cs[0].cpu().numpy().astype(np.float64), cs[1].cpu().numpy().astype(np.float64)
+    x, y = rb[:, :, 0].copy(), rb[:, :, 3].copy()
+    rb[:, :, 0] = cc[:, None] * x + ss[:, None] * y
+    rb[:, :, 3] = cc[:, None] * y - ss[:, None] * x
+    assert np.abs(gb - rb).max() <= tol
+
+
+def C_void(t, elem_offset):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr() + elem_offset * t.element_size())
