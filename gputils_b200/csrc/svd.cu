@@ -171,8 +171,9 @@ __device__ __forceinline__ T jwarp_sum(T v) {
     return v;
 }
 
-// JE: rows per lane (n <= 32 * JE)
-template<typename T, int JE>
+// JE: rows per lane (n <= 32 * JE). FULL: n == 32 * JE (even, no bye, every lane owns JE rows of every column): the row / pair guards
+// of the round loop are compile-time true (BASELINE config 4: n = 128, JE = 4)
+template<typename T, int JE, bool FULL>
 __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A, size_t lda, size_t sA, T *S, size_t sS, T *Vt, size_t ldvt,
                                                   size_t sVt, T *Ur, size_t sUr, int want_u, int *info, size_t batch, int ldx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
                                 p = round + i; p -= p >= npad - 1 ? npad - 1 : 0;
                                 q = round - i; q += q < 0 ? npad - 1 : 0;
                             }
-                            if (p >= n || q >= n) { p = -1; q = -1; }      // bye
+                            if (!FULL && (p >= n || q >= n)) { p = -1; q = -1; }      // bye
                             else if (p > q) { const int t = p; p = q; q = t; }
                         }
                         pp[u] = p; qq[u] = q;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
 #pragma unroll
                         for (int e = 0; e < JE; e++) {
                             const int r = lane + 32 * e;
-                            const bool ok = p >= 0 && r < n;
+                            const bool ok = FULL || (p >= 0 && r < n);
                             cu[u][e] = ok ? X[(size_t) p * ldx + r] : T(0);
                             cv[u][e] = ok ? X[(size_t) q * ldx + r] : T(0);
                             aa = fma(cu[u][e], cu[u][e], aa);
@@ -275,17 +276,17 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
 #pragma unroll
                             for (int e = 0; e < JE; e++) {
                                 const int r = lane + 32 * e;
-                                if (r < n) {
-                                    xp[r] = cu_ * cu[u][e] - su_ * cv[u][e];
-                                    xq[r] = su_ * cu[u][e] + cu_ * cv[u][e];
+                                if (FULL || r < n) {   // explicit fma: this file is compiled with --fmad=false (three instructions per entry otherwise)
+                                    xp[r] = fma(cu_, cu[u][e], -(su_ * cv[u][e]));
+                                    xq[r] = fma(su_, cu[u][e], cu_ * cv[u][e]);
                                 }
                             }
                             if (want_u) {
                                 T *jp = J + (size_t) pp[u] * n, *jq = J + (size_t) qq[u] * n;
                                 for (int r = lane; r < n; r += 32) {
                                     const T ju = jp[r], jv = jq[r];
-                                    jp[r] = cu_ * ju - su_ * jv;
-                                    jq[r] = su_ * ju + cu_ * jv;
+                                    jp[r] = fma(cu_, ju, -(su_ * jv));
+                                    jq[r] = fma(su_, ju, cu_ * jv);
                                 }
                             }
                         }
@@ -613,8 +614,9 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         const bool accumulate = want_u && (ldvt != n || usm > (size_t) ctx->max_smem_optin - 1024);
 #define GPUB_JACOBI_LAUNCH(JEV)                                                                                              \
     {                                                                                                                         \
-        GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_rt<T, JEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));         \
-        k_jacobi_rt<T, JEV><<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, accumulate ? 1 : 0, info, \
+        auto kern = (n == (size_t) 32 * JEV) ? k_jacobi_rt<T, JEV, true> : k_jacobi_rt<T, JEV, false>;                        \
+        GPUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));                       \
+        kern<<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, accumulate ? 1 : 0, info, \
                                                          batch, (int) ldx);                                                   \
     }
         if (n <= 128) GPUB_JACOBI_LAUNCH(4)
