@@ -369,12 +369,14 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // N N^T = U2 U2^T = I - U1 U1^T with U1 = U(:, 0:r): per matrix the kernel takes whichever side has FEWER columns (rank r read from
 // the device) -- A = N with k = n - r columns, or Ualt = U with k = r columns, alpha = -1 and the identity added in the epilogue.
 // For a fat 128 x 1024 matrix (r = 128) that is 128 instead of 896 columns: 7 x fewer flops for the same projector.
-template<bool TRB, int DKT, int WARPS = 8, bool SYM = false, bool PROJ = false>
+// EPI_E (plain NN): C = E + alpha A B with E = blockdiag(Ublk, I) generated in the epilogue (Ublk: ne x ne per matrix, passed through the
+// `Ualt` / `sU` / `rank`-less parameters): the U assembly of Svd / Nullspace then neither initialises nor re-reads the m x m result.
+template<bool TRB, int DKT, int WARPS = 8, bool SYM = false, bool PROJ = false, bool EPI_E = false>
 __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, size_t k, double alpha, const double *__restrict__ A,
                                                     size_t lda, size_t sA, const double *__restrict__ B, size_t ldb, size_t sB,
                                                     double beta, double *C, size_t ldc, size_t sC, size_t tiles_m,
                                                     size_t tiles_n, size_t batch, const unsigned *__restrict__ rank = nullptr,
-                                                    const double *__restrict__ Ualt = nullptr, size_t sU = 0) {
+                                                    const double *__restrict__ Ualt = nullptr, size_t sU = 0, size_t ne = 0) {
     // As[buf][kk][row] (A panel, 16 x 64), Bs[buf][col][kk] (B panel stored k-contiguous per column)
     constexpr int BROWS = TRB ? DKT : 64, BLD = TRB ? DLD : DKT + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -486,6 +488,12 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
                 if (PROJ) {
                     *p0 = alpha * acc[i][j][0] + ((comp && gr == gc) ? 1.0 : 0.0);
                     *p1 = alpha * acc[i][j][1] + ((comp && gr == gc + 1) ? 1.0 : 0.0);
+                } else if (EPI_E) {
+                    const double *ub = Ualt + b * sU;
+                    const double e0 = (gr < ne && gc < ne) ? ub[gr + gc * ne] : (gr == gc ? 1.0 : 0.0);
+                    const double e1 = (gr < ne && gc + 1 < ne) ? ub[gr + (gc + 1) * ne] : (gr == gc + 1 ? 1.0 : 0.0);
+                    *p0 = fma(alpha, acc[i][j][0], e0);
+                    *p1 = fma(alpha, acc[i][j][1], e1);
                 } else if (beta == 0.0) {
                     *p0 = alpha * acc[i][j][0];
                     *p1 = alpha * acc[i][j][1];
@@ -1120,6 +1128,25 @@ bool try_aat_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const d
     k_gemm_dmma<true, 16, 8, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP, tm, tm, batch);
     return true;
 }
+
+} // namespace
+
+// C_i = blockdiag(Ublk_i, I) + alpha A_i B_i (fp64, m, n multiples of 64, k a multiple of 16): used by the U assembly in svd.cu
+int gpub_internal_gemm_plus_e_f64(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, double alpha, const double *A, size_t lda, size_t sA,
+                                  const double *B, size_t ldb, size_t sB, const double *Ublk, size_t ne, size_t sUblk, double *C, size_t ldc,
+                                  size_t sC, size_t batch) {
+    if (m % 64 || n % 64 || k % DK || k < DK || (lda & 1) || (ldb & 1) || (sA & 1) || (sB & 1) || ((((uintptr_t) A) | ((uintptr_t) B)) & 15u))
+        return GPUB_ENOTSUP;
+    GPUB_ENTER(ctx, sidx);
+    const size_t tm = m / 64, tn = n / 64, total = tm * tn * batch, cap = (size_t) ctx->sm_count * 8;
+    constexpr size_t smem16 = sizeof(double) * (2 * 16 * DLD + 2 * 64 * (16 + 4));
+    k_gemm_dmma<false, 16, 4, false, false, true><<<(unsigned) (total < cap ? total : cap), 128, smem16, stream>>>(
+        m, n, k, alpha, A, lda, sA, B, ldb, sB, 0.0, C, ldc, sC, tm, tn, batch, nullptr, Ublk, sUblk, ne);
+    GPUB_LAUNCH_CHECK();
+    return GPUB_OK;
+}
+
+namespace {
 
 template<typename T>
 bool try_projector_dmma(gpub_ctx_t, cudaStream_t, size_t, const T *, size_t, const unsigned *, const T *, size_t, T *, size_t, size_t) { return false; }

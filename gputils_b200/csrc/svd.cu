@@ -13,6 +13,10 @@
 #include "common.cuh"
 #include "svd_small.cuh"
 
+int gpub_internal_gemm_plus_e_f64(gpub_ctx_t ctx, int sidx, size_t m, size_t n, size_t k, double alpha, const double *A, size_t lda, size_t sA,
+                                  const double *B, size_t ldb, size_t sB, const double *Ublk, size_t ne, size_t sUblk, double *C, size_t ldc,
+                                  size_t sC, size_t batch);   // gemm.cu
+
 namespace {
 
 template<typename T>
@@ -553,6 +557,14 @@ int internal_transpose(gpub_ctx_t c, int s, size_t m, size_t n, const float *A, 
 
 inline size_t per_matrix_work_elems(size_t n) { return 3 * n * n + 8 * n + 8; }
 
+inline int wy_final_gemm(gpub_ctx_t ctx, int sidx, size_t m, size_t n, const double *V, size_t lda, size_t sA, const double *Y, const double *Ur, size_t sUr,
+                         double *U, size_t ldu, size_t sU, size_t batch) {
+    return gpub_internal_gemm_plus_e_f64(ctx, sidx, m, m, n, -1.0, V, lda, sA, Y, n, m * n, Ur, n, sUr, U, ldu, sU, batch);
+}
+inline int wy_final_gemm(gpub_ctx_t, int, size_t, size_t, const float *, size_t, size_t, const float *, const float *, size_t, float *, size_t, size_t, size_t) {
+    return GPUB_ENOTSUP;   // the block-reflector assembly is fp64 only (use_wy_assembly)
+}
+
 // U = Q blockdiag(Ur, I) through one block reflector (see k_make_v / k_tfactor): fp64 shapes the tensor-pipe GEMM tiles cover
 template<typename T>
 inline bool use_wy_assembly(size_t m, size_t n) { return sizeof(T) == 8 && n > 32 && n <= 128 && m % 64 == 0 && n % 64 == 0; }
@@ -640,10 +652,11 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
             GPUB_LAUNCH_CHECK();
         }
         if (want_u) {
-            size_t total = m * m * batch;
-            unsigned grid = (unsigned) (gpub_ceil_div(total, 256) < 8192 ? gpub_ceil_div(total, 256) : 8192);
-            k_init_u<T><<<grid, 256, 0, stream>>>((int) m, (int) n, Urj, per, U, ldu, sU, batch);
-            GPUB_LAUNCH_CHECK();
+            auto init_u = [&]() {
+                size_t total = m * m * batch;
+                unsigned grid = (unsigned) (gpub_ceil_div(total, 256) < 8192 ? gpub_ceil_div(total, 256) : 8192);
+                k_init_u<T><<<grid, 256, 0, stream>>>((int) m, (int) n, Urj, per, U, ldu, sU, batch);
+            };
             const size_t tsm = (n * (n + 1) + n) * sizeof(T);
             if (use_wy_assembly<T>(m, n) && lda == m && (sA & 1) == 0 && (ldu & 1) == 0 && (sU & 1) == 0 &&
                 ((((uintptr_t) A) | ((uintptr_t) U)) & 15u) == 0 && tsm <= (size_t) ctx->max_smem_optin) {
@@ -666,9 +679,12 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
                     e = internal_gemm(ctx, sidx, n, m - n, n, T(1), Tw, n, n * n, VtW + n * n, n, m * n, T(0), Yw + n * n, n, m * n, batch);
                     if (e) return e;
                 }
-                e = internal_gemm(ctx, sidx, m, m, n, T(-1), A, lda, sA, Yw, n, m * n, T(1), U, ldu, sU, batch);           // U = E - V Y
+                // U = E - V Y, E = blockdiag(Ur, I) generated in the GEMM's epilogue: the m x m result is written once and never read
+                e = wy_final_gemm(ctx, sidx, m, n, A, lda, sA, Yw, Urj, per, U, ldu, sU, batch);
                 if (e) return e;
             } else {
+                init_u();
+                GPUB_LAUNCH_CHECK();
                 e = internal_ormqr<T>(ctx, sidx, 0, m, m, n, A, lda, sA, tauj, per, U, ldu, sU, batch);
                 if (e) return e;
             }
