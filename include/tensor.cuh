@@ -16,5 +16,6 @@
 #include "gpub200/dtensor.cuh"
 #include "gpub200/factorisers.cuh"
 #include "gpub200/sharded.cuh" /* additive: mats axis sharded over the GPUs of one box */
+#include "gpub200/pitched.cuh" /* additive: per-matrix 128-byte-aligned (padded) storage for shapes that are not multiples of 128 B */
 
 #endif /* TENSOR_CUH */

@@ -196,7 +196,30 @@ def main():
         x = b.transpose(1, 2)[:4]; r = torch.linalg.norm(torch.bmm(a0[:4].transpose(1, 2), x)) / torch.linalg.norm(b0[:4])
         assert float(r) < (1e-10 if dt == "f64" else 1e-3), float(r)
 
+    def pitch(n, dt, batch):
+        """dense (stride n*n) against 128-byte pitched storage for a shape that is not a multiple of 128 B: potrf + potrs through the strided C ABI"""
+        tdt = torch.float64 if dt == "f64" else torch.float32
+        s = 8 if dt == "f64" else 4
+        A0 = torch.empty((batch, n, n), dtype=tdt, device="cuda"); capi.fill_spd_batched(ctx, A0, float(n), 2)
+        b0 = torch.empty((batch, n), dtype=tdt, device="cuda"); capi.fill_uniform(ctx, b0, -1.0, 1.0, 3)
+        info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        for name, stride in (("dense", n * n), ("pitched128", (n * n * s + 127) // 128 * 128 // s)):
+            bs = n if name == "dense" else (n * s + 127) // 128 * 128 // s
+            buf0 = torch.zeros((batch, stride), dtype=tdt, device="cuda"); buf0[:, : n * n] = A0.view(batch, n * n)
+            rhs0 = torch.zeros((batch, bs), dtype=tdt, device="cuda"); rhs0[:, :n] = b0
+            buf = torch.empty_like(buf0); rhs = torch.empty_like(rhs0)
+            def run():
+                ctx.call("potrf_batched", buf, n, capi._p(buf), n, stride, capi._p(info), batch)
+                ctx.call("potrs_batched", buf, n, capi._p(buf), n, stride, capi._p(rhs), bs, batch)
+            def restore():
+                buf.copy_(buf0); rhs.copy_(rhs0)
+            med, best = timeit(run, restore, args.reps)
+            report("potrf+potrs_" + name, [n, n], dt, batch, med, best, 3 * n * n * s + 2 * n * s + 4, n ** 3 / 3 + 2 * n * n)
+
     sc = args.scale
+    if "pitch" in ops:
+        pitch(5, "f64", int(4_000_000 * sc))
+        pitch(10, "f32", int(2_000_000 * sc))
     if "potrf" in ops or "potrs" in ops:
         chol(32, "f64", int(1_000_000 * sc))
     if "cholsweep" in ops:

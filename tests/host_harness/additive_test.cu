@@ -326,8 +326,51 @@ static void givensBatchCase(size_t m, size_t n, size_t k, double tol, const char
     report((std::string("givens_batch_bad_index_throws_") + tag).c_str(), threw);
 }
 
+// PitchedDTensor: matrices on 128-byte boundaries; results equal the dense DTensor path, the padding is never written
+template<typename T>
+static void pitchedCase(size_t n, size_t k, double tol, const char *tag) {
+    std::vector<T> a = spdBatch<T>(n, k, 61 + n), b = uniform<T>(n * k, 62), c = uniform<T>(n * n * k, 63);
+    DTensor<T> A1(a, n, n, k), b1(b, n, 1, k), C1(c, n, n, k), P1(n, n, k);
+    P1.addAB(A1, C1, T(0.5), T(0));
+    CholeskyBatchFactoriser<T> f1(A1);
+    f1.factorise();
+    f1.solve(b1);
+    std::vector<T> L1, x1, p1;
+    A1.download(L1); b1.download(x1); P1.download(p1);
+
+    PitchedDTensor<T> A2(a, n, n, k), b2(b, n, 1, k), C2(c, n, n, k), P2(n, n, k, true);
+    const bool aligned = (A2.matStride() * sizeof(T)) % 128 == 0 && (b2.matStride() * sizeof(T)) % 128 == 0 &&
+                         ((uintptr_t) A2.matrix(k - 1)) % 128 == 0 && A2.matStride() >= n * n;
+    report((std::string("pitched_matrices_start_on_128_byte_boundaries_") + tag).c_str(), aligned, "stride=" + std::to_string(A2.matStride()));
+    P2.addAB(A2, C2, T(0.5), T(0));
+    PitchedCholeskyBatchFactoriser<T> f2(A2);
+    f2.factorise();
+    f2.solve(b2);
+    std::vector<T> L2, x2, p2;
+    A2.download(L2); b2.download(x2); P2.download(p2);
+    std::vector<int> i1, i2;
+    f1.info().download(i1); f2.info().download(i2);
+    report((std::string("pitched_cholesky_equals_dense_") + tag).c_str(), relDiff(L2, L1) <= tol && relDiff(x2, x1) <= 10 * tol && i1 == i2,
+           "rel_L=" + sci(relDiff(L2, L1)) + " rel_x=" + sci(relDiff(x2, x1)));
+    report((std::string("pitched_addAB_equals_dense_") + tag).c_str(), relDiff(p2, p1) <= tol, "rel=" + sci(relDiff(p2, p1)));
+    // padding: P2 was zero-initialised, so every byte between the matrices must still be zero; round trip through toDense / fromDense
+    std::vector<T> flat(P2.matStride() * k);
+    gpuErrChk(cudaMemcpy(flat.data(), P2.raw(), flat.size() * sizeof(T), cudaMemcpyDeviceToHost));
+    bool clean = true;
+    for (size_t i = 0; i < k; i++)
+        for (size_t e = n * n; e < P2.matStride(); e++) clean = clean && flat[i * P2.matStride() + e] == T(0);
+    DTensor<T> dense = P2.toDense();
+    PitchedDTensor<T> back = PitchedDTensor<T>::fromDense(dense);
+    std::vector<T> p3;
+    back.download(p3);
+    report((std::string("pitched_padding_untouched_and_round_trip_") + tag).c_str(), clean && p3 == p2);
+}
+
 int main() {
     Session::setStreams(3);
+    pitchedCase<double>(5, 1000, 1e-14, "f64_5x5");
+    pitchedCase<float>(10, 333, 1e-6, "f32_10x10");
+    pitchedCase<double>(3, 4097, 1e-14, "f64_3x3");
     givensBatchCase<double>(6, 5, 37, 1e-14, "f64_6x5x37");
     givensBatchCase<float>(9, 4, 300, 2e-6, "f32_9x4x300");
     hostPipelineCase<double>(32, 5000, 7, false, "f64_32_pageable");
