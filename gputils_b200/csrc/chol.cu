@@ -250,6 +250,16 @@ __global__ void __launch_bounds__(128) k_potrs8_f32(const float *__restrict__ L,
     }
 }
 
+// Fused solve + all-gather (GATHER): every solution is also stored straight into the gathered tensor of up to 8 devices
+// (peers.x[p] + (peers.offset + matrix) * peers.stride, NVLink peer stores from inside the kernel), so the all-gather that would
+// follow the solve of a sharded batch (SURVEY.md 8e) costs no second pass and no second launch.
+template<typename T>
+struct PotrsPeers {
+    T *x[8];
+    int count;
+    size_t offset, stride;
+};
+
 // ------------------------------------------------------------------------------------------
 // potrf, n == 32 (BASELINE config 2) or 16, dense: k_potrf_pair<T, N>. N / 2 lanes per matrix, lane p owns rows p AND p + N / 2.
 // k_potrf_group<T, 32> (lane = row) executes 31 - j FMA instructions per column step for every row, although row i only
@@ -681,16 +691,6 @@ __global__ void __launch_bounds__(256) k_potrf_cta(int n, T *A, size_t lda, size
 #define GPUB_POTRS_MINB 5
 #endif
 
-// Fused solve + all-gather (GATHER): every solution is also stored straight into the gathered tensor of up to 8 devices
-// (peers.x[p] + (peers.offset + matrix) * peers.stride, NVLink peer stores from inside the kernel), so the all-gather that would
-// follow the solve of a sharded batch (SURVEY.md 8e) costs no second pass and no second launch.
-template<typename T>
-struct PotrsPeers {
-    T *x[8];
-    int count;
-    size_t offset, stride;
-};
-
 template<typename T, int NP, bool DENSE, bool GATHER = false>
 __global__ void __launch_bounds__(GPUB_POTRS_THREADS, GPUB_POTRS_MINB)
 k_potrs_group(int n, const T *__restrict__ L, size_t ldl_rt, size_t strideL, T *b, size_t strideB, size_t batch, PotrsPeers<T> peers) {
@@ -779,80 +779,126 @@ __device__ __forceinline__ T transpose_reduce32(T (&p)[32], int lane) {
 // ------------------------------------------------------------------------------------------
 // Pieces shared by k_potrs_pair64 and k_potrs_quad128: a 64 x 64 lower-triangular block held by one warp as row pairs
 // (lane p: rows p and p + 32), already row-scaled to the strictly lower part of Lb = D^-1 L.
-template<typename T>
-__device__ __forceinline__ void pair64_load_scaled(const T *l_g, size_t ldl, int nloc, int p, T (&lo)[32], T (&hi)[64], T &ilo, T &ihi) {
-    // l_g points at the block's (0, 0) entry; rows >= nloc are an identity pad
-    const bool lo_ok = p < nloc, hi_ok = p + 32 < nloc;
+template<typename T, int H>
+__device__ __forceinline__ void pair64_load_scaled(const T *l_g, size_t ldl, int nloc, int p, T (&lo)[H], T (&hi)[2 * H], T &ilo, T &ihi) {
+    // l_g points at the block's (0, 0) entry; rows >= nloc are an identity pad. H lanes per block (H = 32: a warp per 64 x 64 block;
+    // H = 16 / 8: two / four 32 x 32 / 16 x 16 matrices per warp), lane p of the group owns rows p and p + H
+    const bool lo_ok = p < nloc, hi_ok = p + H < nloc;
 #pragma unroll
-    for (int c = 0; c < 32; c++) lo[c] = (c <= p && lo_ok) ? l_g[p + c * ldl] : T(c == p ? 1 : 0);
+    for (int c = 0; c < H; c++) lo[c] = (c <= p && lo_ok) ? l_g[p + c * ldl] : T(c == p ? 1 : 0);
 #pragma unroll
-    for (int c = 0; c < 64; c++) hi[c] = (c <= p + 32 && hi_ok) ? l_g[p + 32 + c * ldl] : T(c == p + 32 ? 1 : 0);
+    for (int c = 0; c < 2 * H; c++) hi[c] = (c <= p + H && hi_ok) ? l_g[p + H + c * ldl] : T(c == p + H ? 1 : 0);
     T dlo = T(1), dhi = T(1);
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
+    for (int c = 0; c < H; c++) {
         if (c == p) dlo = lo[c];
-        if (c == p) dhi = hi[c + 32];
+        if (c == p) dhi = hi[c + H];
     }
     ilo = T(1) / dlo;
     ihi = T(1) / dhi;
 #pragma unroll
-    for (int c = 0; c < 32; c++) lo[c] = c < p ? lo[c] * ilo : T(0);
+    for (int c = 0; c < H; c++) lo[c] = c < p ? lo[c] * ilo : T(0);
 #pragma unroll
-    for (int c = 0; c < 64; c++) hi[c] = c < p + 32 ? hi[c] * ihi : T(0);
+    for (int c = 0; c < 2 * H; c++) hi[c] = c < p + H ? hi[c] * ihi : T(0);
 }
 
-// Lb y = x (x already scaled by D^-1); on exit xlo, xhi hold y
-template<typename T>
-__device__ __forceinline__ void pair64_forward(const T (&lo)[32], const T (&hi)[64], T &xlo, T &xhi) {
+// Lb y = x (x already scaled by D^-1); on exit xlo, xhi hold y. Shuffles stay inside the group of H lanes.
+template<typename T, int H>
+__device__ __forceinline__ void pair64_forward(const T (&lo)[H], const T (&hi)[2 * H], T &xlo, T &xhi) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const T yj = __shfl_sync(0xffffffffu, xlo, j);
+    for (int j = 0; j < H; j++) {
+        const T yj = __shfl_sync(0xffffffffu, xlo, j, H);
         xlo = fma(-lo[j], yj, xlo);
         xhi = fma(-hi[j], yj, xhi);
     }
 #pragma unroll
-    for (int j = 32; j < 63; j++) {
-        const T yj = __shfl_sync(0xffffffffu, xhi, j - 32);
+    for (int j = H; j < 2 * H - 1; j++) {
+        const T yj = __shfl_sync(0xffffffffu, xhi, j - H, H);
         xhi = fma(-hi[j], yj, xhi);
     }
 }
 
-// Lb^T v = x; on exit xlo, xhi hold v (the caller multiplies by D^-1). tile: the warp's [32][33] scratch
-template<typename T>
-__device__ __forceinline__ void pair64_backward(const T (&lo)[32], const T (&hi)[64], T &xlo, T &xhi, T (*tile)[33], int p) {
+// Lb^T v = x; on exit xlo, xhi hold v (the caller multiplies by D^-1). tile: the group's [H][H + 1] scratch
+template<typename T, int H>
+__device__ __forceinline__ void pair64_backward(const T (&lo)[H], const T (&hi)[2 * H], T &xlo, T &xhi, T (*tile)[H + 1], int p) {
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; c++) tile[p][c] = hi[32 + c];
+    for (int c = 0; c < H; c++) tile[p][c] = hi[H + c];
     __syncwarp();
     {
-        T cb[32];
+        T cb[H];
 #pragma unroll
-        for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+        for (int r = 0; r < H; r++) cb[r] = tile[r][p];
 #pragma unroll
-        for (int jj = 31; jj > 0; jj--) {
-            const T vj = __shfl_sync(0xffffffffu, xhi, jj);
+        for (int jj = H - 1; jj > 0; jj--) {
+            const T vj = __shfl_sync(0xffffffffu, xhi, jj, H);
             xhi = fma(-cb[jj], vj, xhi);
         }
     }
     {
-        T pr[32];
+        T pr[H];
 #pragma unroll
-        for (int c = 0; c < 32; c++) pr[c] = hi[c] * xhi;
-        TReduce<T, 32, 16>::run(pr, p);
+        for (int c = 0; c < H; c++) pr[c] = hi[c] * xhi;
+        TReduce<T, H, H / 2>::run(pr, p);
         xlo -= pr[0];
     }
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; c++) tile[p][c] = lo[c];
+    for (int c = 0; c < H; c++) tile[p][c] = lo[c];
     __syncwarp();
     {
-        T cb[32];
+        T cb[H];
 #pragma unroll
-        for (int r = 0; r < 32; r++) cb[r] = tile[r][p];
+        for (int r = 0; r < H; r++) cb[r] = tile[r][p];
 #pragma unroll
-        for (int jj = 31; jj > 0; jj--) {
-            const T vj = __shfl_sync(0xffffffffu, xlo, jj);
+        for (int jj = H - 1; jj > 0; jj--) {
+            const T vj = __shfl_sync(0xffffffffu, xlo, jj, H);
             xlo = fma(-cb[jj], vj, xlo);
+        }
+    }
+}
+
+// potrs, n == 32 or 16, dense: k_potrs_pair<T, N>, N / 2 lanes per matrix (two / four matrices per warp), the layout and the pieces of
+// k_potrs_pair64. Against the lane = row kernel (k_potrs_group, a warp per 32 x 32 matrix) every shuffle, shared-memory store and
+// load of the substitution serves two (four) matrices: the kernel is bound by LSU wavefronts (ncu: 84 % busy), 124 of the ~320 per
+// matrix being the 62 64-bit shuffles of the two sweeps.
+#ifndef GPUB_POTRS_PAIR
+#define GPUB_POTRS_PAIR 1
+#endif
+#ifndef GPUB_POTRS_PAIR16
+#define GPUB_POTRS_PAIR16 1
+#endif
+template<typename T, int N, bool GATHER>
+__global__ void __launch_bounds__(128, 4) k_potrs_pair(const T *__restrict__ L, size_t strideL, T *b, size_t strideB, size_t batch, PotrsPeers<T> peers) {
+    constexpr int H = N / 2, GROUPS = 128 / H;
+    __shared__ T s_t[GROUPS][H][H + 1];
+    const int grp = threadIdx.x / H, p = threadIdx.x % H;
+    const size_t ngroups = (size_t) gridDim.x * GROUPS;
+    const size_t iters = (batch + ngroups - 1) / ngroups;
+    for (size_t it = 0; it < iters; it++) {
+        size_t mat = it * ngroups + (size_t) blockIdx.x * GROUPS + grp;
+        const bool live = mat < batch;
+        if (!live) mat = batch - 1;
+        T *b_g = b + mat * strideB;
+        T lo[H], hi[N], ilo, ihi;
+        pair64_load_scaled<T>(L + mat * strideL, (size_t) N, N, p, lo, hi, ilo, ihi);
+        T xlo = b_g[p] * ilo, xhi = b_g[p + H] * ihi;
+        pair64_forward<T>(lo, hi, xlo, xhi);
+        pair64_backward<T>(lo, hi, xlo, xhi, s_t[grp], p);
+        xlo *= ilo;
+        xhi *= ihi;
+        if (live) {
+            b_g[p] = xlo;
+            b_g[p + H] = xhi;
+            if (GATHER) {
+#pragma unroll
+                for (int pr = 0; pr < 8; pr++)
+                    if (pr < peers.count) {
+                        T *o = peers.x[pr] + (peers.offset + mat) * peers.stride;
+                        o[p] = xlo;
+                        o[p + H] = xhi;
+                    }
+            }
         }
     }
 }
@@ -1129,6 +1175,23 @@ int potrs_batched(gpub_ctx_t ctx, int sidx, size_t n, const T *L, size_t ldl, si
         GPUB_LAUNCH_CHECK();
         return GPUB_OK;
     }
+#if GPUB_POTRS_PAIR
+    if ((n == 32 || (GPUB_POTRS_PAIR16 && n == 16)) && ldl == n && strideB >= n) {
+        // two (four) matrices per warp, row pairs in registers
+        const size_t want = gpub_ceil_div(batch, (size_t) (256 / n)), cap = (size_t) ctx->sm_count * 4 * GPUB_GRID_WAVES;
+        const unsigned grid = (unsigned) (want < cap ? want : cap);
+        const PotrsPeers<T> none = PotrsPeers<T>();
+        if (n == 32) {
+            if (peers) k_potrs_pair<T, 32, true><<<grid, 128, 0, stream>>>(L, strideL, b, strideB, batch, *peers);
+            else k_potrs_pair<T, 32, false><<<grid, 128, 0, stream>>>(L, strideL, b, strideB, batch, none);
+        } else {
+            if (peers) k_potrs_pair<T, 16, true><<<grid, 128, 0, stream>>>(L, strideL, b, strideB, batch, *peers);
+            else k_potrs_pair<T, 16, false><<<grid, 128, 0, stream>>>(L, strideL, b, strideB, batch, none);
+        }
+        GPUB_LAUNCH_CHECK();
+        return GPUB_OK;
+    }
+#endif
     if (n <= 32) {
         const int np = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
         const size_t groups = GPUB_POTRS_THREADS / np;
