@@ -727,7 +727,7 @@ def main():
                              "(SURVEY.md 8e)") % strong_ms
 
     # ---- end to end through host buffers --------------------------------------------------------------------
-    e2e = e2e_dropin = None
+    e2e = e2e_dropin = e2e_lower = None
     A_host = b_host = None
     want_host = (not args.no_e2e) or (rank == 0 and not args.no_cpu)
     if want_host:
@@ -742,25 +742,38 @@ def main():
         d2h = x_host.numel() * 8 + info_host.numel() * 4
         if not is_ref:
             # the product's host call: three streams, chunks of the batch flow upload -> factorise + solve -> download
-            def e2e_step():
-                arm.capi.chol_solve_from_host(arm.ctx, A, b, info, A_host, b_host, x_host, info_host, chunks=16)
-            e2e_step(); torch.cuda.synchronize()
-            if use_dist:
-                dist.barrier()
-            t0 = time.perf_counter()
-            s, e = _ev(), _ev()
-            s.record()
-            for _ in range(e2e_steps):
-                e2e_step()                                   # blocking: returns when x and info are on the host
-            e.record(); torch.cuda.synchronize()
-            wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-            e2e_ms = reduce_max(max(s.elapsed_time(e) / e2e_steps, wall_ms))
-            assert int(info_host.abs().max()) == 0
-            assert torch.equal(x_host[:1024], b[:1024].cpu())
+            def time_host_call(lower_only):
+                def e2e_step():
+                    arm.capi.chol_solve_from_host(arm.ctx, A, b, info, A_host, b_host, x_host, info_host, chunks=16, lower_only=lower_only)
+                e2e_step(); torch.cuda.synchronize()
+                if use_dist:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                s, e = _ev(), _ev()
+                s.record()
+                for _ in range(e2e_steps):
+                    e2e_step()                               # blocking: returns when x and info are on the host
+                e.record(); torch.cuda.synchronize()
+                wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+                ms = reduce_max(max(s.elapsed_time(e) / e2e_steps, wall_ms))
+                assert int(info_host.abs().max()) == 0
+                assert torch.equal(x_host[:1024], b[:1024].cpu())
+                return ms
+            e2e_ms = time_host_call(False)
             e2e = {"value": eff_world * k / (e2e_ms * 1e-3), "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_ms, "steps": e2e_steps,
                    "path": "gpub_chol_solve_from_host_f64 (CholeskyBatchFactoriser::factoriseAndSolveFromHost): pinned host buffers, 16 chunks, "
-                           "upload / factorise + solve / download on three streams"}
+                           "upload / factorise + solve / download on three streams; every byte of A and b is transferred"}
+            # the same call with GPUB_LOWER_ONLY: the factorisation reads the lower triangle, so the 16 x 16 block above the diagonal
+            # of every matrix is not put on the wire (75 % of A's bytes; h2d_bytes_per_step counts what is actually copied). Reported
+            # beside the headline e2e, which moves full matrices like the reference arm.
+            x_host.zero_()
+            low_ms = time_host_call(True)
+            e2e_lower = {"value": eff_world * k / (low_ms * 1e-3), "unit": "matrices/s",
+                         "h2d_bytes_per_step": (n * (n // 2) + (n // 2) * (n // 2)) * 8 * k + b_host.numel() * 8, "d2h_bytes_per_step": d2h,
+                         "ms_per_step": low_ms, "steps": e2e_steps,
+                         "path": "as e2e with lowerTriangleOnly: of every matrix the block wholly above the diagonal is not transferred "
+                                 "(strided DMA; the factorisation never reads it)"}
         if eff_world == 1:
             # the reference-shaped sequence from pageable memory: upload(A), upload(b), factorise, solve, download(x), download(info)
             import numpy as np
@@ -858,6 +871,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "e2e_dropin": e2e_dropin,
+            "e2e_lower_only": e2e_lower,
             "strong": strong,
             "allgather": allgather,
             "sharded_api": sharded_api,

@@ -300,9 +300,13 @@ def nullspace_project(ctx: Context, P, b):
     gemm_batched(ctx, b, P, b)
 
 
-def chol_solve_from_host(ctx: Context, A, b, info, A_host, b_host, x_host, info_host, chunks: int = 16, sidx: int = 0):
+LOWER_ONLY = 1 << 32   # GPUB_LOWER_ONLY
+
+
+def chol_solve_from_host(ctx: Context, A, b, info, A_host, b_host, x_host, info_host, chunks: int = 16, sidx: int = 0, lower_only: bool = False):
     """The product's host pipeline (gpub_chol_solve_from_host_*): upload / factorise + solve / download of successive chunks
     overlap on three streams. A, b, info are device tensors (k, n, n) / (k, 1, n) / (k,); the host tensors may be pinned."""
     k, n = A.shape[0], A.shape[1]
     hp = lambda t: _vp(t.data_ptr()) if t is not None else None
-    ctx.call("chol_solve_from_host", A, n, _p(A), hp(b), hp(info), hp(A_host), hp(b_host), hp(x_host), hp(info_host), k, chunks, sidx=sidx)
+    ctx.call("chol_solve_from_host", A, n, _p(A), hp(b), hp(info), hp(A_host), hp(b_host), hp(x_host), hp(info_host), k,
+             chunks | (LOWER_ONLY if lower_only else 0), sidx=sidx)

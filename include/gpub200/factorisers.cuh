@@ -402,15 +402,19 @@ public:
      * hide behind the upload of the next. hostA holds the matrices (numRows^2 values each, column-major, mats slowest), hostB the
      * right-hand sides; pinned host memory is DMA'd directly, pageable memory is staged. On return the factorised tensor holds
      * the factors (as after factorise()), `b` and hostX the solutions, info() -- and hostInfo, if given -- the status codes.
+     * lowerTriangleOnly: the factorisation never reads above the diagonal, so the block of each matrix that lies wholly above it is
+     * not transferred (pinned hostA, fp64 n >= 32 / fp32 n >= 64, even n): 75 % of the bytes; that block of the tensor keeps its
+     * previous content instead of the input's.
      */
     void factoriseAndSolveFromHost(const T *hostA, const T *hostB, DTensor<T> &b, T *hostX, int *hostInfo = nullptr,
-                                   size_t chunks = 16) {
+                                   size_t chunks = 16, bool lowerTriangleOnly = false) {
         if (m_factorisationDone) throw std::logic_error("[CholeskyBatch] already factorised");
         if (m_numRows != b.numRows() || m_numMats != b.numMats() || b.numCols() != 1)
             throw std::invalid_argument("[CholeskyBatch] A and b incompatible");
         if (!hostA || !hostB) throw std::invalid_argument("[CholeskyBatch] null host buffer");
         gpuErrChk(gpub200::Abi<T>::chol_from_host(gpub200::ctx(), (int) m_matrix->streamIdx(), m_numRows, m_matrix->raw(), b.raw(),
-                                                  m_info->raw(), hostA, hostB, hostX, hostInfo, m_numMats, chunks));
+                                                  m_info->raw(), hostA, hostB, hostX, hostInfo, m_numMats,
+                                                  chunks | (lowerTriangleOnly ? GPUB_LOWER_ONLY : 0)));
         m_factorisationDone = true;
     }
 };

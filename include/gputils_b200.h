@@ -193,7 +193,12 @@ int gpub_potrs_allgather_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const f
  * each piece is uploaded into A_dev / b_dev, factorised and solved as soon as it has landed, and x / info are downloaded behind
  * the kernels, on three streams (upload, stream `sidx`, download), so the whole job runs at the host link's speed. On return
  * (blocking) A_dev holds the factors, b_dev and x_host the solutions, info_dev / info_host the status codes. b_* / x_host /
- * info_* may be NULL (factorise only / no download). Host buffers may be pinned (DMA'd directly) or pageable (staged). */
+ * info_* may be NULL (factorise only / no download). Host buffers may be pinned (DMA'd directly) or pageable (staged).
+ * `chunks` may be OR-ed with GPUB_LOWER_ONLY: the factorisation reads the lower triangle only, so for pinned A_host and rows of the
+ * half-height strip of at least 128 bytes (fp64: even n >= 32) the n/2 x n/2 block above the diagonal is not transferred (75 % of
+ * the bytes, strided DMA); that block of A_dev then keeps whatever it held. Without the flag every byte of A_host is copied. */
+#define GPUB_LOWER_ONLY ((size_t) 1 << 32)
+#define GPUB_CHUNKS_MASK (((size_t) 1 << 32) - 1)
 int gpub_chol_solve_from_host_f64(gpub_ctx_t ctx, int sidx, size_t n, double *A_dev, double *b_dev, int *info_dev,
                                   const double *A_host, const double *b_host, double *x_host, int *info_host,
                                   size_t batch, size_t chunks);

@@ -440,6 +440,18 @@ def test_host_pipeline_equals_potrf_potrs(gpu_ctx, oracle, dt, n, batch, pinned)
     info2 = torch.zeros(batch, dtype=torch.int32, device="cuda")
     capi.chol_solve_from_host(gpu_ctx, dA2, db2, info2, hA, hb, hx, hi, chunks=7)
     ok = (info.cpu() == 0)
+    if pinned:
+        # GPUB_LOWER_ONLY: the block wholly above the diagonal is not transferred (when its rows are >= 128 bytes) -- same factors and
+        # solutions, and that block of the device tensor keeps what it held
+        dA3 = torch.full((batch, n, n), 777.0, dtype=tdt, device="cuda"); db3 = torch.empty_like(db2); info3 = torch.zeros_like(info2)
+        hx3 = torch.empty_like(hx); hi3 = torch.empty_like(hi)
+        capi.chol_solve_from_host(gpu_ctx, dA3, db3, info3, hA, hb, hx3, hi3, chunks=5, lower_only=True)
+        low3 = torch.triu(torch.ones(n, n)).bool()
+        assert torch.equal(info3.cpu(), info2.cpu()) and torch.equal(hi3, hi)
+        assert torch.equal(dA3.cpu()[ok][:, low3], dA2.cpu()[ok][:, low3]) and torch.equal(db3.cpu()[ok], db2.cpu()[ok]) and torch.equal(hx3[ok], hx[ok])
+        skipped = (n // 2) * dA3.element_size() >= 128
+        blk = dA3[:, n // 2:, : n // 2]                       # [mat][col >= n/2][row < n/2]
+        assert bool((blk == 777.0).all()) == skipped
     assert torch.equal(info.cpu(), info2.cpu()) and torch.equal(info2.cpu(), hi) and int(hi[batch // 2]) == 1
     low = torch.triu(torch.ones(n, n)).bool()
     assert torch.equal(dA.cpu()[ok][:, low], dA2.cpu()[ok][:, low])
