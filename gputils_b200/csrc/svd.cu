@@ -175,6 +175,121 @@ __device__ __forceinline__ T jwarp_sum(T v) {
     return v;
 }
 
+// Tail of the Jacobi kernels: X (shared memory, column p at X + p * ldx) holds the orthogonalised columns W D. Singular values = column
+// norms, sorted descending; Vt rows = normalised columns; columns without a singular value (rank deficiency) are replaced by an
+// orthonormal completion so that Vt is always orthogonal (Nullspace relies on it). NT = threads of the CTA.
+template<typename T, int NT>
+__device__ __forceinline__ void jacobi_finish(int n, int ldx, T *X, T *s_sig, T *s_coef, int *s_perm, T *s_val, int *s_idx, T *s_g, T *vt_g,
+                                              size_t ldvt, T *J, int want_u) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = NT / 32;
+    constexpr int JT = NT;
+    // column norms
+    for (int p = warp; p < n; p += NW) {
+        T aa = 0;
+        for (int r = lane; r < n; r += 32) aa = fma(X[(size_t) p * ldx + r], X[(size_t) p * ldx + r], aa);
+        aa = jwarp_sum(aa);
+        if (lane == 0) s_sig[p] = sqrt(aa);
+    }
+    __syncthreads();
+    // rank sort, descending (ties broken by column index)
+    for (int p = tid; p < n; p += JT) {
+        const T sp = s_sig[p];
+        int rank = 0;
+        for (int q = 0; q < n; q++) {
+            const T sq = s_sig[q];
+            rank += (sq > sp || (sq == sp && q < p)) ? 1 : 0;
+        }
+        s_perm[rank] = p;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += JT) s_g[i] = s_sig[s_perm[i]];
+    const T smax = s_sig[s_perm[0]];
+    const T thr = smax * (T) n * (T) JacobiEps<T>::v;
+    // normalise the columns that carry a singular value; count them
+    int nfull = 0;
+    for (int i = 0; i < n; i++) nfull += (s_sig[s_perm[i]] > thr) ? 1 : 0;   // sorted: the first nfull positions
+    for (int i = warp; i < nfull; i += NW) {
+        T *xp = X + (size_t) s_perm[i] * ldx;
+        const T inv = T(1) / s_sig[s_perm[i]];
+        for (int r = lane; r < n; r += 32) xp[r] *= inv;
+    }
+    __syncthreads();
+    // orthonormal completion of the null columns, one at a time
+    for (int i = nfull; i < n; i++) {
+        T *xz = X + (size_t) s_perm[i] * ldx;
+        // pick the unit vector e_k with the largest component outside span(final columns): 1 - sum_w w[k]^2
+        T best = T(-1);
+        int bestk = 0;
+        for (int k = tid; k < n; k += JT) {
+            T acc = T(1);
+            for (int w = 0; w < i; w++) {
+                const T x = X[(size_t) s_perm[w] * ldx + k];
+                acc = fma(-x, x, acc);
+            }
+            if (acc > best) { best = acc; bestk = k; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+            if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bestk; }
+        __syncthreads();
+        best = s_val[0]; bestk = s_idx[0];
+        for (int w = 1; w < NW; w++)
+            if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bestk)) { best = s_val[w]; bestk = s_idx[w]; }
+        __syncthreads();
+        for (int r = tid; r < n; r += JT) xz[r] = (r == bestk) ? T(1) : T(0);
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {     // project out the final columns, twice
+            // coefficients g_w = w . z, one final column per warp iteration
+            for (int w = warp; w < i; w += NW) {
+                const T *xw = X + (size_t) s_perm[w] * ldx;
+                T g = 0;
+                for (int r = lane; r < n; r += 32) g = fma(xw[r], xz[r], g);
+                g = jwarp_sum(g);
+                if (lane == 0) s_coef[w] = g;
+            }
+            __syncthreads();
+            for (int r = tid; r < n; r += JT) {
+                T acc = xz[r];
+                for (int w = 0; w < i; w++) acc = fma(-s_coef[w], X[(size_t) s_perm[w] * ldx + r], acc);
+                xz[r] = acc;
+            }
+            __syncthreads();
+        }
+        T nn = 0;
+        for (int r = tid; r < n; r += JT) nn = fma(xz[r], xz[r], nn);
+        nn = jwarp_sum(nn);
+        if (lane == 0) s_val[warp] = nn;
+        __syncthreads();
+        T tot = 0;
+        for (int w = 0; w < NW; w++) tot += s_val[w];
+        __syncthreads();
+        const T inv = T(1) / sqrt(tot);
+        for (int r = tid; r < n; r += JT) xz[r] *= inv;
+        __syncthreads();
+    }
+    for (int e = tid; e < n * n; e += JT) {
+        const int i = e % n, c = e / n;             // Vt(i, c) = W(c, perm i)
+        vt_g[i + (size_t) c * ldvt] = X[(size_t) s_perm[i] * ldx + c];
+    }
+    if (want_u) {
+        // Ur(:, i) = J(:, perm i): permute the columns in place through shared memory (X is free now)
+        __syncthreads();
+        for (int e = tid; e < n * n; e += JT) {
+            const int r = e % n, i = e / n;
+            X[(size_t) i * ldx + r] = J[(size_t) s_perm[i] * n + r];
+        }
+        __syncthreads();
+        for (int e = tid; e < n * n; e += JT) {
+            const int r = e % n, i = e / n;
+            J[(size_t) i * n + r] = X[(size_t) i * ldx + r];
+        }
+    }
+}
+
 // JE: rows per lane (n <= 32 * JE). FULL: n == 32 * JE (even, no bye, every lane owns JE rows of every column): the row / pair guards
 // of the round loop are compile-time true (BASELINE config 4: n = 128, JE = 4)
 template<typename T, int JE, bool FULL>
@@ -303,112 +418,173 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
             if (s_rot == 0) break;
             __syncthreads();
         }
-        // column norms
-        for (int p = warp; p < n; p += NW) {
-            T aa = 0;
-            for (int r = lane; r < n; r += 32) aa = fma(X[(size_t) p * ldx + r], X[(size_t) p * ldx + r], aa);
-            aa = jwarp_sum(aa);
-            if (lane == 0) s_sig[p] = sqrt(aa);
-        }
+        jacobi_finish<T, JT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, J, want_u);
+        if (tid == 0 && info) info[mat] = sweep >= 40 ? 1 : 0;
         __syncthreads();
-        // rank sort, descending (ties broken by column index)
-        for (int p = tid; p < n; p += JT) {
-            const T sp = s_sig[p];
-            int rank = 0;
-            for (int q = 0; q < n; q++) {
-                const T sq = s_sig[q];
-                rank += (sq > sp || (sq == sp && q < p)) ? 1 : 0;
-            }
-            s_perm[rank] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_jacobi_blk<T, JE>: the same one-sided Jacobi for n = 32 JE (64, 96, 128: BASELINE config 4), columns resident in REGISTERS.
+// k_jacobi_rt moves every column shared memory -> registers -> shared memory in every round (2 n^2 s bytes per round: 2048 cycles of
+// shared-memory bandwidth at n = 128, fp64), recomputes both column norms of every pair and meets a CTA barrier per round. Here the
+// columns are grouped into half-blocks of 4; a warp holds TWO half-blocks (8 columns, JE rows per lane) and the ordering has two
+// levels: the round-robin (circle) schedule runs over the 2 NW half-blocks -- 2 NW - 1 block-rounds per sweep, one CTA barrier and one
+// trip of the columns through shared memory per BLOCK-round -- and inside a block-round the warp rotates the 16 cross pairs of its
+// two half-blocks in 4 rounds of 4 disjoint pairs without leaving its registers (plus, in the first block-round of a sweep, the
+// 2 x 6 pairs inside each half-block in 3 rounds): the same n (n - 1) / 2 pairs per sweep in the same number of 4-pair rounds, with a
+// quarter of the shared-memory traffic and barriers. Column norms are computed once per block-round and carried through its
+// rotations by a' = a - t c, b' = b + t c (exact for the rotation that annihilates c; at most 7 updates before the next
+// recomputation), so a round needs ONE dot product per pair instead of three.
+// Convergence: a sweep without a rotation, or -- quadratic convergence -- a sweep in which every rotated pair had both cos^2 and
+// tan^2 of its angle below tol / (16 n): such rotations change the other cosines by less than n cos tan < tol, the threshold under
+// which a pair is not rotated at all (the angle is tested too: between columns of equal norm a tiny cosine still asks for a large
+// rotation, which would carry first-order changes to the neighbours).
+// ------------------------------------------------------------------------------------------
+template<typename T, int JE, int X0, int Y0, int X1, int Y1, int X2, int Y2, int X3, int Y3>
+__device__ __forceinline__ void jblk_round(T (&c)[8][JE], T (&nn)[8], int lane, T tol2, T quad2, unsigned &flags) {
+    T d[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int e = 0; e < JE; e++) {
+        d[0] = fma(c[X0][e], c[Y0][e], d[0]);
+        d[1] = fma(c[X1][e], c[Y1][e], d[1]);
+        d[2] = fma(c[X2][e], c[Y2][e], d[2]);
+        d[3] = fma(c[X3][e], c[Y3][e], d[3]);
+    }
+    TReduce<T, 4, 16>::run(d, lane);                  // lane l: total of value l / 8
+    const int u = lane & 3;
+    const T cc = __shfl_sync(0xffffffffu, d[0], 8 * u);
+    // lane u (mod 4) computes the rotation of pair u: one instruction stream for the four pairs
+    const T aa = u == 0 ? nn[X0] : (u == 1 ? nn[X1] : (u == 2 ? nn[X2] : nn[X3]));
+    const T bb = u == 0 ? nn[Y0] : (u == 1 ? nn[Y1] : (u == 2 ? nn[Y2] : nn[Y3]));
+    T cs = T(1), sn = T(0), dl = T(0), tt = T(0);
+    bool rot = false;
+    const T c2 = cc * cc, ab = aa * bb;
+    if (cc != T(0) && !(c2 <= tol2 * ab)) {
+        const T zeta = (bb - aa) * jac_rcp<T>(T(2) * cc);
+        const T az = fabs(zeta);
+        T t;
+        if (az > JacobiEps<T>::big) {
+            t = jac_rcp<T>(T(2) * az);
+        } else {
+            const T w = fma(zeta, zeta, T(1));
+            t = jac_rcp<T>(fma(w, jac_rsqrt<T>(w), az));
         }
-        __syncthreads();
-        T *s_g = S + mat * sS;
-        for (int i = tid; i < n; i += JT) s_g[i] = s_sig[s_perm[i]];
-        const T smax = s_sig[s_perm[0]];
-        const T thr = smax * (T) n * (T) JacobiEps<T>::v;
-        // normalise the columns that carry a singular value; count them
-        int nfull = 0;
-        for (int i = 0; i < n; i++) nfull += (s_sig[s_perm[i]] > thr) ? 1 : 0;   // sorted: the first nfull positions
-        for (int i = warp; i < nfull; i += NW) {
-            T *xp = X + (size_t) s_perm[i] * ldx;
-            const T inv = T(1) / s_sig[s_perm[i]];
-            for (int r = lane; r < n; r += 32) xp[r] *= inv;
+        t = zeta >= T(0) ? t : -t;
+        tt = t * t;
+        cs = jac_rsqrt<T>(tt + T(1));
+        sn = cs * t;
+        dl = t * cc;
+        rot = true;
+    }
+    const unsigned rmask = __ballot_sync(0xffffffffu, rot) & 0xfu;
+    const unsigned big = __ballot_sync(0xffffffffu, rot && (!(c2 <= quad2 * ab) || tt > quad2)) & 0xfu;
+    flags |= (rmask ? 1u : 0u) | (big ? 2u : 0u);
+#define GPUB_JBLK_APPLY(U, XI, YI)                                                                                   \
+    if ((rmask >> U) & 1u) {                                                                                         \
+        const T cu_ = __shfl_sync(0xffffffffu, cs, U), su_ = __shfl_sync(0xffffffffu, sn, U);                        \
+        const T dl_ = __shfl_sync(0xffffffffu, dl, U);                                                               \
+        _Pragma("unroll") for (int e = 0; e < JE; e++) {                                                             \
+            const T x = c[XI][e], y = c[YI][e];                                                                      \
+            c[XI][e] = fma(cu_, x, -(su_ * y));                                                                      \
+            c[YI][e] = fma(su_, x, cu_ * y);                                                                         \
+        }                                                                                                            \
+        nn[XI] -= dl_;                                                                                               \
+        nn[YI] += dl_;                                                                                               \
+    }
+    GPUB_JBLK_APPLY(0, X0, Y0)
+    GPUB_JBLK_APPLY(1, X1, Y1)
+    GPUB_JBLK_APPLY(2, X2, Y2)
+    GPUB_JBLK_APPLY(3, X3, Y3)
+#undef GPUB_JBLK_APPLY
+}
+
+template<typename T, int JE>
+__global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A, size_t lda, size_t sA, T *S, size_t sS, T *Vt, size_t ldvt,
+                                                         size_t sVt, int *info, size_t batch, int ldx) {
+    constexpr int n = 32 * JE, NT = 128 * JE, NW = NT / 32, NH = 2 * NW;   // NW warps, NH half-blocks of 4 columns
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *X = reinterpret_cast<T *>(smem_raw);            // [n][ldx]
+    T *s_sig = X + (size_t) n * ldx;
+    T *s_coef = s_sig + n;
+    int *s_perm = reinterpret_cast<int *>(s_coef + n);
+    __shared__ unsigned s_flags;
+    __shared__ T s_val[NW];
+    __shared__ int s_idx[NW];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T tol = (T) JacobiEps<T>::v * sqrt((T) n);
+    const T tol2 = tol * tol;
+    const T quad2 = tol / (T) (16 * n);
+
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        const T *a_g = A + mat * sA;
+        for (int e = tid; e < n * n; e += NT) {
+            const int p = e / n, r = e % n;              // X(r, p) = R(p, r)
+            X[(size_t) p * ldx + r] = (p <= r) ? a_g[p + (size_t) r * lda] : T(0);
         }
+        if (tid == 0) s_flags = 0;
         __syncthreads();
-        // orthonormal completion of the null columns, one at a time
-        for (int i = nfull; i < n; i++) {
-            T *xz = X + (size_t) s_perm[i] * ldx;
-            // pick the unit vector e_k with the largest component outside span(final columns): 1 - sum_w w[k]^2
-            T best = T(-1);
-            int bestk = 0;
-            for (int k = tid; k < n; k += JT) {
-                T acc = T(1);
-                for (int w = 0; w < i; w++) {
-                    const T x = X[(size_t) s_perm[w] * ldx + k];
-                    acc = fma(-x, x, acc);
+        int sweep = 0;
+        for (; sweep < 40; sweep++) {
+            unsigned flags = 0;
+            for (int br = 0; br < NH - 1; br++) {
+                // circle method over the half-blocks: warp 0 keeps half-block NH - 1, the others meet (br + w, br - w) mod (NH - 1)
+                int ha, hb;
+                if (warp == 0) { ha = NH - 1; hb = br; }
+                else {
+                    ha = br + warp; ha -= ha >= NH - 1 ? NH - 1 : 0;
+                    hb = br - warp; hb += hb < 0 ? NH - 1 : 0;
                 }
-                if (acc > best) { best = acc; bestk = k; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const T ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
-                if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
-            }
-            if (lane == 0) { s_val[warp] = best; s_idx[warp] = bestk; }
-            __syncthreads();
-            best = s_val[0]; bestk = s_idx[0];
-            for (int w = 1; w < NW; w++)
-                if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bestk)) { best = s_val[w]; bestk = s_idx[w]; }
-            __syncthreads();
-            for (int r = tid; r < n; r += JT) xz[r] = (r == bestk) ? T(1) : T(0);
-            __syncthreads();
-            for (int pass = 0; pass < 2; pass++) {     // project out the final columns, twice
-                // coefficients g_w = w . z, one final column per warp iteration
-                for (int w = warp; w < i; w += NW) {
-                    const T *xw = X + (size_t) s_perm[w] * ldx;
-                    T g = 0;
-                    for (int r = lane; r < n; r += 32) g = fma(xw[r], xz[r], g);
-                    g = jwarp_sum(g);
-                    if (lane == 0) s_coef[w] = g;
+                T c[8][JE], nn[8];
+                T *xa = X + (size_t) (4 * ha) * ldx + lane, *xb = X + (size_t) (4 * hb) * ldx + lane;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+#pragma unroll
+                    for (int e = 0; e < JE; e++) {
+                        c[v][e] = xa[(size_t) v * ldx + 32 * e];
+                        c[4 + v][e] = xb[(size_t) v * ldx + 32 * e];
+                    }
+                }
+                {
+                    T red[8];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) {
+                        red[v] = T(0);
+#pragma unroll
+                        for (int e = 0; e < JE; e++) red[v] = fma(c[v][e], c[v][e], red[v]);
+                    }
+                    TReduce<T, 8, 16>::run(red, lane);    // lane l: total of value l / 4
+#pragma unroll
+                    for (int v = 0; v < 8; v++) nn[v] = __shfl_sync(0xffffffffu, red[0], 4 * v);
+                }
+                if (br == 0) {
+                    jblk_round<T, JE, 0, 1, 2, 3, 4, 5, 6, 7>(c, nn, lane, tol2, quad2, flags);
+                    jblk_round<T, JE, 0, 2, 1, 3, 4, 6, 5, 7>(c, nn, lane, tol2, quad2, flags);
+                    jblk_round<T, JE, 0, 3, 1, 2, 4, 7, 5, 6>(c, nn, lane, tol2, quad2, flags);
+                }
+                jblk_round<T, JE, 0, 4, 1, 5, 2, 6, 3, 7>(c, nn, lane, tol2, quad2, flags);
+                jblk_round<T, JE, 0, 5, 1, 6, 2, 7, 3, 4>(c, nn, lane, tol2, quad2, flags);
+                jblk_round<T, JE, 0, 6, 1, 7, 2, 4, 3, 5>(c, nn, lane, tol2, quad2, flags);
+                jblk_round<T, JE, 0, 7, 1, 4, 2, 5, 3, 6>(c, nn, lane, tol2, quad2, flags);
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+#pragma unroll
+                    for (int e = 0; e < JE; e++) {
+                        xa[(size_t) v * ldx + 32 * e] = c[v][e];
+                        xb[(size_t) v * ldx + 32 * e] = c[4 + v][e];
+                    }
                 }
                 __syncthreads();
-                for (int r = tid; r < n; r += JT) {
-                    T acc = xz[r];
-                    for (int w = 0; w < i; w++) acc = fma(-s_coef[w], X[(size_t) s_perm[w] * ldx + r], acc);
-                    xz[r] = acc;
-                }
-                __syncthreads();
             }
-            T nn = 0;
-            for (int r = tid; r < n; r += JT) nn = fma(xz[r], xz[r], nn);
-            nn = jwarp_sum(nn);
-            if (lane == 0) s_val[warp] = nn;
+            if (flags && lane == 0) atomicOr(&s_flags, flags);
             __syncthreads();
-            T tot = 0;
-            for (int w = 0; w < NW; w++) tot += s_val[w];
+            const unsigned f = s_flags;
             __syncthreads();
-            const T inv = T(1) / sqrt(tot);
-            for (int r = tid; r < n; r += JT) xz[r] *= inv;
-            __syncthreads();
+            if (tid == 0) s_flags = 0;
+            if (!(f & 2u)) { sweep += (f & 1u) ? 1 : 0; break; }     // no rotation, or only negligible ones: converged
         }
-        T *vt_g = Vt + mat * sVt;
-        for (int e = tid; e < n * n; e += JT) {
-            const int i = e % n, c = e / n;             // Vt(i, c) = W(c, perm i)
-            vt_g[i + (size_t) c * ldvt] = X[(size_t) s_perm[i] * ldx + c];
-        }
-        if (want_u) {
-            // Ur(:, i) = J(:, perm i): permute the columns in place through shared memory (X is free now)
-            __syncthreads();
-            for (int e = tid; e < n * n; e += JT) {
-                const int r = e % n, i = e / n;
-                X[(size_t) i * ldx + r] = J[(size_t) s_perm[i] * n + r];
-            }
-            __syncthreads();
-            for (int e = tid; e < n * n; e += JT) {
-                const int r = e % n, i = e / n;
-                J[(size_t) i * n + r] = X[(size_t) i * ldx + r];
-            }
-        }
+        __syncthreads();
+        jacobi_finish<T, NT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, (T *) nullptr, 0);
         if (tid == 0 && info) info[mat] = sweep >= 40 ? 1 : 0;
         __syncthreads();
     }
@@ -631,7 +807,18 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         kern<<<jgrid, JT, smem, stream>>>((int) n, A, lda, sA, S, sS, Vt, ldvt, sVt, Urj, per, accumulate ? 1 : 0, info, \
                                                          batch, (int) ldx);                                                   \
     }
-        if (n <= 128) GPUB_JACOBI_LAUNCH(4)
+        if (!accumulate && (n == 64 || n == 96 || n == 128)) {
+            // columns resident in registers, two-level ordering (k_jacobi_blk)
+#define GPUB_JBLK_LAUNCH(JEV)                                                                                                \
+    {                                                                                                                         \
+        GPUB_CUDA(cudaFuncSetAttribute(k_jacobi_blk<T, JEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));       \
+        k_jacobi_blk<T, JEV><<<jgrid, 128 * JEV, smem, stream>>>(A, lda, sA, S, sS, Vt, ldvt, sVt, info, batch, (int) ldx);  \
+    }
+            if (n == 64) GPUB_JBLK_LAUNCH(2)
+            else if (n == 96) GPUB_JBLK_LAUNCH(3)
+            else GPUB_JBLK_LAUNCH(4)
+#undef GPUB_JBLK_LAUNCH
+        } else if (n <= 128) GPUB_JACOBI_LAUNCH(4)
         else if (n <= 192) GPUB_JACOBI_LAUNCH(6)
         else if (n <= 256) GPUB_JACOBI_LAUNCH(8)
         else return GPUB_ENOTSUP;

@@ -182,7 +182,7 @@ def _subspace_gap(U1, U2):
 @pytest.mark.parametrize("m,n,batch,want_u", [(3, 2, 3, True), (8, 3, 4, True), (4, 3, 3, False), (3, 3, 5, True), (64, 16, 40, True),
                                               (64, 32, 3, True), (200, 20, 3, True), (200, 20, 3, False), (500, 8, 2, True),
                                               (128, 64, 2, True), (256, 40, 3, False), (100, 33, 2, True), (300, 128, 1, True),
-                                              (1024, 128, 2, False)])
+                                              (1024, 128, 2, False), (192, 96, 2, True), (256, 64, 5, False), (128, 128, 3, True)])
 def test_gesvd_batched(gpu_ctx, oracle, dt, m, n, batch, want_u):
     from gputils_b200 import capi
     rng = np.random.default_rng(7 * m + n)
@@ -228,6 +228,27 @@ def test_gesvd_rank_deficient_factors_stay_orthogonal(gpu_ctx, oracle, dt, m, n)
     # the trailing m - rank columns of U span the orthogonal complement of range(A)
     r = n - dup
     assert np.abs(Un[:, :, r:].transpose(0, 2, 1) @ A.astype(np.float64)).max() <= 1e3 * tol * So.max()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n", [(128, 64), (256, 128)])
+def test_gesvd_clustered_singular_values(gpu_ctx, dt, m, n):
+    """Multiple singular values (half of them 2, half 1, and the identity-like case of all equal): between columns of equal norm a
+    tiny cosine still asks for a large rotation, the case the early-exit rule of k_jacobi_blk has to leave alone."""
+    from gputils_b200 import capi
+    rng = np.random.default_rng(m * n)
+    Q, _ = np.linalg.qr(rng.normal(size=(m, n))); V, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    s1 = np.ones(n); s1[: n // 2] = 2.0
+    A = np.stack([(Q * s1) @ V.T, Q @ V.T, (Q * np.linspace(3.0, 1.0, n)) @ V.T]).astype(dt)
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), True)
+    tol = 100 * TOL[np.dtype(dt)]
+    assert not info.cpu().numpy().any()
+    Sn = S.cpu().numpy().astype(np.float64); Un = host(U).astype(np.float64); Vn = host(Vt).astype(np.float64)
+    So = np.stack([np.linalg.svd(A[i].astype(np.float64), compute_uv=False) for i in range(3)])
+    assert np.abs(Sn - So).max() <= tol * So.max()
+    assert np.abs(Vn @ Vn.transpose(0, 2, 1) - np.eye(n)).max() <= tol
+    assert np.abs(Un.transpose(0, 2, 1) @ Un - np.eye(m)).max() <= tol
+    assert rel_err(Un[:, :, :n] * Sn[:, None, :] @ Vn, A) <= tol
 
 
 @pytest.mark.parametrize("dt", DTYPES)
