@@ -167,6 +167,15 @@ template<> __device__ __forceinline__ double jac_rcp<double>(double x) {
     return fma(fma(-x, y, 1.0), y, y);
 }
 template<> __device__ __forceinline__ float jac_rcp<float>(float x) { return __frcp_rn(x); }
+// two Newton steps: relative error ~1e-12 (fp64), for quantities that do not need the last bits
+template<typename T> __device__ __forceinline__ T jac_rcp2(T x);
+template<> __device__ __forceinline__ double jac_rcp2<double>(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    return fma(fma(-x, y, 1.0), y, y);
+}
+template<> __device__ __forceinline__ float jac_rcp2<float>(float x) { return __frcp_rn(x); }
 
 template<typename T>
 __device__ __forceinline__ T jwarp_sum(T v) {
@@ -441,6 +450,75 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
 // which a pair is not rotated at all (the angle is tested too: between columns of equal norm a tiny cosine still asks for a large
 // rotation, which would carry first-order changes to the neighbours).
 // ------------------------------------------------------------------------------------------
+// Rotation of one pair from its squared norms aa, bb and dot product cc: cs, sn, the norm transfer dl = t cc, tt = t^2.
+// t = sign(d) g / (|d| + sqrt(d^2 + g^2)) with d = bb - aa, g = 2 cc -- one rsqrt and one reciprocal instead of the two reciprocals
+// and the rsqrt of the textbook form through zeta = d / g; the rotation stays orthogonal to working precision for ANY t because
+// cs = (1 + t^2)^(-1/2) and sn = cs t are computed to full accuracy from the t actually used (an inexact t only leaves a residual
+// of relative size eps in the pair's dot product). The textbook path serves d^2 + g^2 outside the normal range.
+template<typename T>
+__device__ __forceinline__ bool jblk_params(T aa, T bb, T cc, T tol2, T &cs, T &sn, T &dl, T &tt, T &c2, T &ab) {
+    cs = T(1); sn = T(0); dl = T(0); tt = T(0);
+    c2 = cc * cc; ab = aa * bb;
+    if (cc == T(0) || c2 <= tol2 * ab) return false;
+    const T d = bb - aa, g = cc + cc;
+    const T h2 = fma(d, d, g * g);
+    T t;
+    if (h2 < JacobiEps<T>::big && h2 > T(1) / JacobiEps<T>::big) {
+        const T r = jac_rsqrt<T>(h2);
+        const T den = fma(h2, r, fabs(d));            // |d| + sqrt(d^2 + g^2)
+        t = g * jac_rcp2<T>(den);
+        t = d >= T(0) ? t : -t;
+    } else {
+        const T zeta = d * jac_rcp<T>(g);
+        const T az = fabs(zeta);
+        if (az > JacobiEps<T>::big) t = jac_rcp<T>(T(2) * az);
+        else {
+            const T w = fma(zeta, zeta, T(1));
+            t = jac_rcp<T>(fma(w, jac_rsqrt<T>(w), az));
+        }
+        t = zeta >= T(0) ? t : -t;
+    }
+    tt = t * t;
+    cs = jac_rsqrt<T>(tt + T(1));
+    sn = cs * t;
+    dl = t * cc;
+    return true;
+}
+
+// Cross round S of a block-round: pairs (a_u, b_((u + S) mod 4)), u = 0..3, a_u = c[u], b_v = c[4 + v]. Lane u (mod 4) computes pair u and
+// OWNS the two norms it needs: nA = |a_u|^2 stays with it through the four rounds, nB = |b_((u + S) mod 4)|^2 moves on to the lane that
+// meets that column next (one shuffle per round), so the carried norms cost no broadcast and no select.
+template<typename T, int JE, int S>
+__device__ __forceinline__ void jblk_cross(T (&c)[8][JE], T &nA, T &nB, int lane, T tol2, T quad2, unsigned &flags) {
+    T d[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int e = 0; e < JE; e++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) d[u] = fma(c[u][e], c[4 + ((u + S) & 3)][e], d[u]);
+    }
+    TReduce<T, 4, 16>::run(d, lane);                  // lane l: total of value l / 8
+    const T cc = __shfl_sync(0xffffffffu, d[0], 8 * (lane & 3));
+    T cs, sn, dl, tt, c2, ab;
+    const bool rot = jblk_params<T>(nA, nB, cc, tol2, cs, sn, dl, tt, c2, ab);
+    const unsigned rmask = __ballot_sync(0xffffffffu, rot) & 0xfu;
+    flags |= rot ? ((!(c2 <= quad2 * ab) || tt > quad2) ? 3u : 1u) : 0u;
+    nA -= dl;
+    nB += dl;
+    if (rmask) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const T cu_ = __shfl_sync(0xffffffffu, cs, u), su_ = __shfl_sync(0xffffffffu, sn, u);
+#pragma unroll
+            for (int e = 0; e < JE; e++) {
+                const T x = c[u][e], y = c[4 + ((u + S) & 3)][e];
+                c[4 + ((u + S) & 3)][e] = fma(su_, x, cu_ * y);
+                c[u][e] = fma(cu_, x, -(su_ * y));
+            }
+        }
+    }
+    nB = __shfl_sync(0xffffffffu, nB, (lane & ~3) | ((lane + 1) & 3));
+}
+
 template<typename T, int JE, int X0, int Y0, int X1, int Y1, int X2, int Y2, int X3, int Y3>
 __device__ __forceinline__ void jblk_round(T (&c)[8][JE], T (&nn)[8], int lane, T tol2, T quad2, unsigned &flags) {
     T d[4] = {T(0), T(0), T(0), T(0)};
@@ -478,8 +556,7 @@ __device__ __forceinline__ void jblk_round(T (&c)[8][JE], T (&nn)[8], int lane, 
         rot = true;
     }
     const unsigned rmask = __ballot_sync(0xffffffffu, rot) & 0xfu;
-    const unsigned big = __ballot_sync(0xffffffffu, rot && (!(c2 <= quad2 * ab) || tt > quad2)) & 0xfu;
-    flags |= (rmask ? 1u : 0u) | (big ? 2u : 0u);
+    flags |= rot ? ((!(c2 <= quad2 * ab) || tt > quad2) ? 3u : 1u) : 0u;
 #define GPUB_JBLK_APPLY(U, XI, YI)                                                                                   \
     if ((rmask >> U) & 1u) {                                                                                         \
         const T cu_ = __shfl_sync(0xffffffffu, cs, U), su_ = __shfl_sync(0xffffffffu, sn, U);                        \
@@ -535,7 +612,7 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                     ha = br + warp; ha -= ha >= NH - 1 ? NH - 1 : 0;
                     hb = br - warp; hb += hb < 0 ? NH - 1 : 0;
                 }
-                T c[8][JE], nn[8];
+                T c[8][JE];
                 T *xa = X + (size_t) (4 * ha) * ldx + lane, *xb = X + (size_t) (4 * hb) * ldx + lane;
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
@@ -545,6 +622,7 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                         c[4 + v][e] = xb[(size_t) v * ldx + 32 * e];
                     }
                 }
+                T nA, nB;
                 {
                     T red[8];
 #pragma unroll
@@ -554,18 +632,26 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                         for (int e = 0; e < JE; e++) red[v] = fma(c[v][e], c[v][e], red[v]);
                     }
                     TReduce<T, 8, 16>::run(red, lane);    // lane l: total of value l / 4
+                    if (br == 0) {
+                        // first block-round of a sweep: the pairs inside each half-block (three rounds, norms held by every lane)
+                        T nn[8];
 #pragma unroll
-                    for (int v = 0; v < 8; v++) nn[v] = __shfl_sync(0xffffffffu, red[0], 4 * v);
+                        for (int v = 0; v < 8; v++) nn[v] = __shfl_sync(0xffffffffu, red[0], 4 * v);
+                        jblk_round<T, JE, 0, 1, 2, 3, 4, 5, 6, 7>(c, nn, lane, tol2, quad2, flags);
+                        jblk_round<T, JE, 0, 2, 1, 3, 4, 6, 5, 7>(c, nn, lane, tol2, quad2, flags);
+                        jblk_round<T, JE, 0, 3, 1, 2, 4, 7, 5, 6>(c, nn, lane, tol2, quad2, flags);
+                        const int u = lane & 3;
+                        nA = u == 0 ? nn[0] : (u == 1 ? nn[1] : (u == 2 ? nn[2] : nn[3]));
+                        nB = u == 0 ? nn[4] : (u == 1 ? nn[5] : (u == 2 ? nn[6] : nn[7]));
+                    } else {
+                        nA = __shfl_sync(0xffffffffu, red[0], 4 * (lane & 3));
+                        nB = __shfl_sync(0xffffffffu, red[0], 16 + 4 * (lane & 3));
+                    }
                 }
-                if (br == 0) {
-                    jblk_round<T, JE, 0, 1, 2, 3, 4, 5, 6, 7>(c, nn, lane, tol2, quad2, flags);
-                    jblk_round<T, JE, 0, 2, 1, 3, 4, 6, 5, 7>(c, nn, lane, tol2, quad2, flags);
-                    jblk_round<T, JE, 0, 3, 1, 2, 4, 7, 5, 6>(c, nn, lane, tol2, quad2, flags);
-                }
-                jblk_round<T, JE, 0, 4, 1, 5, 2, 6, 3, 7>(c, nn, lane, tol2, quad2, flags);
-                jblk_round<T, JE, 0, 5, 1, 6, 2, 7, 3, 4>(c, nn, lane, tol2, quad2, flags);
-                jblk_round<T, JE, 0, 6, 1, 7, 2, 4, 3, 5>(c, nn, lane, tol2, quad2, flags);
-                jblk_round<T, JE, 0, 7, 1, 4, 2, 5, 3, 6>(c, nn, lane, tol2, quad2, flags);
+                jblk_cross<T, JE, 0>(c, nA, nB, lane, tol2, quad2, flags);
+                jblk_cross<T, JE, 1>(c, nA, nB, lane, tol2, quad2, flags);
+                jblk_cross<T, JE, 2>(c, nA, nB, lane, tol2, quad2, flags);
+                jblk_cross<T, JE, 3>(c, nA, nB, lane, tol2, quad2, flags);
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
 #pragma unroll
@@ -576,7 +662,7 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                 }
                 __syncthreads();
             }
-            if (flags && lane == 0) atomicOr(&s_flags, flags);
+            if (flags) atomicOr(&s_flags, flags);
             __syncthreads();
             const unsigned f = s_flags;
             __syncthreads();
