@@ -485,11 +485,25 @@ __device__ __forceinline__ bool jblk_params(T aa, T bb, T cc, T tol2, T &cs, T &
     return true;
 }
 
+// squared norms of the 8 columns of a warp: lane l gets the norm of column l / 4
+template<typename T, int JE>
+__device__ __forceinline__ void jblk_norms(const T (&c)[8][JE], int lane, T &tot) {
+    T red[8];
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        red[v] = T(0);
+#pragma unroll
+        for (int e = 0; e < JE; e++) red[v] = fma(c[v][e], c[v][e], red[v]);
+    }
+    TReduce<T, 8, 16>::run(red, lane);
+    tot = red[0];
+}
+
 // Cross round S of a block-round: pairs (a_u, b_((u + S) mod 4)), u = 0..3, a_u = c[u], b_v = c[4 + v]. Lane u (mod 4) computes pair u and
 // OWNS the two norms it needs: nA = |a_u|^2 stays with it through the four rounds, nB = |b_((u + S) mod 4)|^2 moves on to the lane that
 // meets that column next (one shuffle per round), so the carried norms cost no broadcast and no select.
 template<typename T, int JE, int S>
-__device__ __forceinline__ void jblk_cross(T (&c)[8][JE], T &nA, T &nB, int lane, T tol2, T quad2, unsigned &flags) {
+__device__ __forceinline__ void jblk_cross(T (&c)[8][JE], T &nA, T &nB, int lane, T tol2, T quad2, unsigned &flags, bool &dirty) {
     T d[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
     for (int e = 0; e < JE; e++) {
@@ -502,6 +516,8 @@ __device__ __forceinline__ void jblk_cross(T (&c)[8][JE], T &nA, T &nB, int lane
     const bool rot = jblk_params<T>(nA, nB, cc, tol2, cs, sn, dl, tt, c2, ab);
     const unsigned rmask = __ballot_sync(0xffffffffu, rot) & 0xfu;
     flags |= rot ? ((!(c2 <= quad2 * ab) || tt > quad2) ? 3u : 1u) : 0u;
+    // a norm that lost more than a decimal digit to cancellation is recomputed from the column at the end of the block-round
+    dirty = dirty || !(nA - dl > T(0.0625) * nA) || !(nB + dl > T(0.0625) * nB);
     nA -= dl;
     nB += dl;
     if (rmask) {
@@ -623,35 +639,39 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                     }
                 }
                 T nA, nB;
-                {
-                    T red[8];
+                bool dirty = false;
+                if (br == 0) {
+                    // first block-round of a sweep: exact norms, then the pairs inside each half-block (three rounds, norms held by every lane)
+                    T nn[8];
+                    jblk_norms<T, JE>(c, lane, nn[0]);
 #pragma unroll
-                    for (int v = 0; v < 8; v++) {
-                        red[v] = T(0);
-#pragma unroll
-                        for (int e = 0; e < JE; e++) red[v] = fma(c[v][e], c[v][e], red[v]);
-                    }
-                    TReduce<T, 8, 16>::run(red, lane);    // lane l: total of value l / 4
-                    if (br == 0) {
-                        // first block-round of a sweep: the pairs inside each half-block (three rounds, norms held by every lane)
-                        T nn[8];
-#pragma unroll
-                        for (int v = 0; v < 8; v++) nn[v] = __shfl_sync(0xffffffffu, red[0], 4 * v);
-                        jblk_round<T, JE, 0, 1, 2, 3, 4, 5, 6, 7>(c, nn, lane, tol2, quad2, flags);
-                        jblk_round<T, JE, 0, 2, 1, 3, 4, 6, 5, 7>(c, nn, lane, tol2, quad2, flags);
-                        jblk_round<T, JE, 0, 3, 1, 2, 4, 7, 5, 6>(c, nn, lane, tol2, quad2, flags);
-                        const int u = lane & 3;
-                        nA = u == 0 ? nn[0] : (u == 1 ? nn[1] : (u == 2 ? nn[2] : nn[3]));
-                        nB = u == 0 ? nn[4] : (u == 1 ? nn[5] : (u == 2 ? nn[6] : nn[7]));
-                    } else {
-                        nA = __shfl_sync(0xffffffffu, red[0], 4 * (lane & 3));
-                        nB = __shfl_sync(0xffffffffu, red[0], 16 + 4 * (lane & 3));
-                    }
+                    for (int v = 7; v >= 0; v--) nn[v] = __shfl_sync(0xffffffffu, nn[0], 4 * v);
+                    jblk_round<T, JE, 0, 1, 2, 3, 4, 5, 6, 7>(c, nn, lane, tol2, quad2, flags);
+                    jblk_round<T, JE, 0, 2, 1, 3, 4, 6, 5, 7>(c, nn, lane, tol2, quad2, flags);
+                    jblk_round<T, JE, 0, 3, 1, 2, 4, 7, 5, 6>(c, nn, lane, tol2, quad2, flags);
+                    const int u = lane & 3;
+                    nA = u == 0 ? nn[0] : (u == 1 ? nn[1] : (u == 2 ? nn[2] : nn[3]));
+                    nB = u == 0 ? nn[4] : (u == 1 ? nn[5] : (u == 2 ? nn[6] : nn[7]));
+                    dirty = true;
+                } else {
+                    // the squared norms travel with the columns (s_sig is free until the tail)
+                    nA = s_sig[4 * ha + (lane & 3)];
+                    nB = s_sig[4 * hb + (lane & 3)];
                 }
-                jblk_cross<T, JE, 0>(c, nA, nB, lane, tol2, quad2, flags);
-                jblk_cross<T, JE, 1>(c, nA, nB, lane, tol2, quad2, flags);
-                jblk_cross<T, JE, 2>(c, nA, nB, lane, tol2, quad2, flags);
-                jblk_cross<T, JE, 3>(c, nA, nB, lane, tol2, quad2, flags);
+                jblk_cross<T, JE, 0>(c, nA, nB, lane, tol2, quad2, flags, dirty);
+                jblk_cross<T, JE, 1>(c, nA, nB, lane, tol2, quad2, flags, dirty);
+                jblk_cross<T, JE, 2>(c, nA, nB, lane, tol2, quad2, flags, dirty);
+                jblk_cross<T, JE, 3>(c, nA, nB, lane, tol2, quad2, flags, dirty);
+                if (__any_sync(0xffffffffu, dirty)) {
+                    T tot;
+                    jblk_norms<T, JE>(c, lane, tot);
+                    nA = __shfl_sync(0xffffffffu, tot, 4 * (lane & 3));
+                    nB = __shfl_sync(0xffffffffu, tot, 16 + 4 * (lane & 3));
+                }
+                if (lane < 4) {
+                    s_sig[4 * ha + lane] = nA;
+                    s_sig[4 * hb + lane] = nB;
+                }
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
 #pragma unroll
