@@ -702,6 +702,7 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                     nA = __shfl_sync(0xffffffffu, tot, 4 * (lane & 3));
                     nB = __shfl_sync(0xffffffffu, tot, 16 + 4 * (lane & 3));
                 }
+                __syncwarp();                               // every lane has read the norms lanes 0..3 are about to replace
                 if (lane < 4) {
                     s_sig[4 * ha + lane] = nA;
                     s_sig[4 * hb + lane] = nB;

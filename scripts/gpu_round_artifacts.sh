@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 ncu --set full --clock-control none -k regex:"k_potrf_pair|k_potrs_group" -s 2 -c 2 -o gpurun_out/${tag}_prof_chol32 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --batch 250000 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_geqrf_tc" -c 1 -o gpurun_out/${tag}_prof_geqrf python scripts/bench_ops.py --ops qr --reps 1 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_gels_f2" -c 1 -o gpurun_out/${tag}_prof_gels python scripts/bench_ops.py --ops gels --reps 1 --scale 0.25 > /dev/null 2>&1
-ncu --set full --clock-control none -k regex:"k_jacobi_rt|k_ormqr_tc|k_gemv|k_gemm_dmma" -c 6 -o gpurun_out/${tag}_prof_svd python scripts/bench_ops.py --ops svdu,nullspace --reps 1 --scale 0.125 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:"k_jacobi_rt|k_jacobi_blk|k_ormqr_tc|k_gemv|k_gemm_dmma" -c 8 -o gpurun_out/${tag}_prof_svd python scripts/bench_ops.py --ops svdu,nullspace --reps 1 --scale 0.125 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_gemm_col" -s 5 -c 1 -o gpurun_out/${tag}_prof_gemm8 python scripts/bench_ops.py --ops gemm --reps 1 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_potrf_pair|k_potrs_pair64|k_potrf_pipe|k_potrs_quad128" -c 8 -o gpurun_out/${tag}_prof_chol64 python scripts/bench_ops.py --ops cholsweep --reps 1 --scale 0.125 > /dev/null 2>&1
 # keep what travels back small (gpurun merges at most 64 MiB): summarise every capture here and drop the .ncu-rep
