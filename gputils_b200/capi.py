@@ -53,6 +53,7 @@ _TYPED = {
     "nullspace_pack_batched": [_sz, _vp, _sz, _vp, _vp, _sz, _sz],
     "aat_batched": [_sz, _vp, _sz, _vp, _sz, _sz],
     "nullspace_projector_batched": [_sz, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _sz],
+    "nullspace_build_batched": [_sz, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _sz],
     "fill_uniform": [_sz, _vp, "T", "T", _u64],
     "fill_spd_batched": [_sz, _vp, _sz, "T", _u64, _sz],
     "chol_solve_from_host": [_sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz],
@@ -290,8 +291,7 @@ def nullspace_build(ctx: Context, a, eps: float = 1e-6):
     rank = count_gt_batched(ctx, S, eps)
     N = torch.empty((k, n, n), dtype=a.dtype, device=a.device)
     P = torch.empty((k, n, n), dtype=a.dtype, device=a.device)
-    ctx.call("nullspace_pack_batched", a, n, _p(U), n * n, _p(rank), _p(N), n * n, k)
-    ctx.call("nullspace_projector_batched", a, n, _p(U), n * n, _p(rank), _p(N), n * n, _p(P), n * n, k)
+    ctx.call("nullspace_build_batched", a, n, _p(U), n * n, _p(rank), _p(N), n * n, _p(P), n * n, k)
     return N, P, rank
 
 

@@ -446,16 +446,22 @@ __global__ void k_nullspace_pack(size_t n, const T *__restrict__ U, size_t sU, c
 }
 
 template<typename T>
-int nullspace_pack(gpub_ctx_t ctx, int sidx, size_t n, const T *U, size_t sU, const unsigned int *rank, T *N, size_t sN,
-                   size_t batch) {
+int nullspace_pack_on(cudaStream_t stream, size_t n, const T *U, size_t sU, const unsigned int *rank, T *N, size_t sN, size_t batch) {
     if (n == 0 || batch == 0) return GPUB_OK;
     if (!U || !rank || !N) return GPUB_EINVAL;
-    GPUB_ENTER(ctx, sidx);
     unsigned gx = (unsigned) (gpub_ceil_div(n * n, 256) < 64 ? gpub_ceil_div(n * n, 256) : 64);
     unsigned gy = (unsigned) (batch < 65535 ? batch : 65535);
     k_nullspace_pack<T><<<dim3(gx, gy), 256, 0, stream>>>(n, U, sU, rank, N, sN, batch);
     GPUB_LAUNCH_CHECK();
     return GPUB_OK;
+}
+
+template<typename T>
+int nullspace_pack(gpub_ctx_t ctx, int sidx, size_t n, const T *U, size_t sU, const unsigned int *rank, T *N, size_t sN,
+                   size_t batch) {
+    if (n == 0 || batch == 0) return GPUB_OK;
+    GPUB_ENTER(ctx, sidx);
+    return nullspace_pack_on<T>(stream, n, U, sU, rank, N, sN, batch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -486,6 +492,17 @@ __global__ void k_fill_spd(size_t n, T *A, size_t sA, double shift, uint64_t see
 }
 
 } // namespace
+
+int gpub_internal_nullspace_pack_f64(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *U, size_t sU, const unsigned int *rank, double *N, size_t sN, size_t batch) {
+    if (!ctx) return GPUB_EINVAL;
+    gpub_device_guard guard(ctx->device);
+    return nullspace_pack_on<double>(stream, n, U, sU, rank, N, sN, batch);
+}
+int gpub_internal_nullspace_pack_f32(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const float *U, size_t sU, const unsigned int *rank, float *N, size_t sN, size_t batch) {
+    if (!ctx) return GPUB_EINVAL;
+    gpub_device_guard guard(ctx->device);
+    return nullspace_pack_on<float>(stream, n, U, sU, rank, N, sN, batch);
+}
 
 extern "C" {
 

@@ -81,6 +81,11 @@ int gpub_h2d(gpub_ctx_t ctx, cudaStream_t stream, void *dst_dev, const void *src
 int gpub_d2h(gpub_ctx_t ctx, cudaStream_t stream, void *dst_host, const void *src_dev, size_t bytes);
 // the two private non-blocking streams of the host pipeline and n cached events
 int gpub_ctx_aux(gpub_ctx_t ctx, cudaStream_t *up, cudaStream_t *down, size_t n_events, cudaEvent_t **events);
+// a private stream to run an independent kernel beside the caller's stream, and two fresh events (timing disabled) for the fork
+// and the join; the caller destroys the events once it has queued the waits (CUDA defers the release until they have completed)
+int gpub_ctx_fork(gpub_ctx_t ctx, cudaStream_t *side, cudaEvent_t ev[2]);
+int gpub_internal_nullspace_pack_f64(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *U, size_t sU, const unsigned int *rank, double *N, size_t sN, size_t batch);
+int gpub_internal_nullspace_pack_f32(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const float *U, size_t sU, const unsigned int *rank, float *N, size_t sN, size_t batch);
 
 #define GPUB_ENTER(ctx, sidx)                              \
     if (!(ctx)) return GPUB_EINVAL;                        \

@@ -403,14 +403,18 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
         const double *bb = B + b * sB + (TRB ? col0 : col0 * ldb);
         size_t kcount = k;
         bool comp = false;
+        int klead = 0;                                    // PROJ, U2 side: columns of the first panel that still belong to U1
         if (PROJ) {
             const size_t r = rank[b] < n ? rank[b] : n;
             comp = r <= n - r;
             kcount = comp ? r : n - r;
-            if (comp) {
-                a = Ualt + b * sU + row0;
-                bb = Ualt + b * sU + col0;
-            }
+            // both sides are read from U itself (the packed basis N is not an input: its packing can run beside this kernel).
+            // U1 = columns 0 .. r-1, panels from column 0, the tail of the last panel masked; U2 = columns r .. n-1, read as whole
+            // panels that END at column n (so nothing is read past the matrix), the head of the first panel masked
+            const size_t c0 = comp ? 0 : n - ((kcount + DKT - 1) / DKT) * DKT;
+            klead = comp ? 0 : (int) (r - c0);
+            a = Ualt + b * sU + row0 + c0 * lda;
+            bb = Ualt + b * sU + col0 + c0 * ldb;
             alpha = comp ? -1.0 : 1.0;
         }
         double acc[MI][4][2];
@@ -459,6 +463,14 @@ __global__ void __launch_bounds__(32 * WARPS) k_gemm_dmma(size_t m, size_t n, si
                 for (int e = threadIdx.x; e < (DKT - kv) * 64; e += NTH) {
                     As[buf][kv + e / 64][e % 64] = 0.0;
                     Bs[buf][kv + e / 64][e % 64] = 0.0;
+                }
+                __syncthreads();
+            }
+            if (PROJ && !comp && p == 0 && klead > 0) {
+                // ... and the columns before the rank that came along with the first panel do not belong to U2
+                for (int e = threadIdx.x; e < klead * 64; e += NTH) {
+                    As[buf][e / 64][e % 64] = 0.0;
+                    Bs[buf][e / 64][e % 64] = 0.0;
                 }
                 __syncthreads();
             }
@@ -1148,15 +1160,19 @@ int gpub_internal_gemm_plus_e_f64(gpub_ctx_t ctx, int sidx, size_t m, size_t n, 
 
 namespace {
 
+// true when the projector is computed from U alone (k_gemm_dmma PROJ): then the packed basis N is not an input of it
+template<typename T> bool projector_reads_u_only(size_t, const T *, size_t) { return false; }
+template<> bool projector_reads_u_only<double>(size_t n, const double *U, size_t sU) { return n % 64 == 0 && !(sU & 1) && !(((uintptr_t) U) & 15u); }
+
 template<typename T>
 bool try_projector_dmma(gpub_ctx_t, cudaStream_t, size_t, const T *, size_t, const unsigned *, const T *, size_t, T *, size_t, size_t) { return false; }
 template<>
 bool try_projector_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, const double *U, size_t sU, const unsigned *rank, const double *N,
                                 size_t sN, double *P, size_t sP, size_t batch) {
-    if (n % 64 != 0 || (sN & 1) || (sU & 1) || ((((uintptr_t) N) | ((uintptr_t) U)) & 15u)) return false;
+    if (!projector_reads_u_only<double>(n, U, sU)) return false;
     const size_t tm = n / 64, total = tm * (tm + 1) / 2 * batch, cap = (size_t) ctx->sm_count * 8;
     constexpr size_t smemT = sizeof(double) * (2 * 16 * DLD + 2 * 16 * DLD);
-    k_gemm_dmma<true, 16, 8, true, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, N, n, sN, N, n, sN, 0.0, P, n, sP,
+    k_gemm_dmma<true, 16, 8, true, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, U, n, sU, U, n, sU, 0.0, P, n, sP,
                                                                                                          tm, tm, batch, rank, U, sU);
     return true;
 }
@@ -1205,5 +1221,51 @@ GPUB_DEF_AAT(f32, float)
     }
 GPUB_DEF_PROJ(f64, double)
 GPUB_DEF_PROJ(f32, float)
+
+/* Nullspace: the packed basis N and the projector N N' from the orthogonal factor in one call. The two kernels are independent
+ * (both read U and the ranks; the projector multiplies out U1 or U2 straight from U), one is a copy and the other a contraction, so
+ * the packing runs on a private stream beside the projector and the call's stream joins it at the end. */
+#define GPUB_DEF_NSBUILD(SUF, T)                                                                                     \
+    int gpub_nullspace_build_batched_##SUF(gpub_ctx_t ctx, int sidx, size_t n, const T *U, size_t sU, const unsigned int *rank, \
+                                           T *N, size_t sN, T *P, size_t sP, size_t batch) {                          \
+        if (n == 0 || batch == 0) return GPUB_OK;                                                                    \
+        if (!N || !P || !U || !rank) return GPUB_EINVAL;                                                             \
+        if (!projector_reads_u_only<T>(n, U, sU)) {   /* N N' is multiplied out from N itself: one after the other */  \
+            const int e = gpub_nullspace_pack_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, batch);                \
+            return e ? e : gpub_nullspace_projector_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, P, sP, batch);   \
+        }                                                                                                            \
+        cudaStream_t side = nullptr;                                                                                 \
+        cudaEvent_t ev[2] = {nullptr, nullptr};                                                                      \
+        {                                                                                                            \
+            GPUB_ENTER(ctx, sidx);                                                                                   \
+            int e = gpub_ctx_fork(ctx, &side, ev);                                                                   \
+            if (e) return e;                                                                                         \
+            cudaError_t fk = cudaEventRecord(ev[0], stream);                                                         \
+            if (fk == cudaSuccess) fk = cudaStreamWaitEvent(side, ev[0], 0);                                         \
+            if (fk != cudaSuccess) {                                                                                 \
+                cudaEventDestroy(ev[0]);                                                                             \
+                cudaEventDestroy(ev[1]);                                                                             \
+                return (int) fk;                                                                                     \
+            }                                                                                                        \
+            e = gpub_internal_nullspace_pack_##SUF(ctx, side, n, U, sU, rank, N, sN, batch);                         \
+            const cudaError_t rr = cudaEventRecord(ev[1], side);                                                     \
+            if (e || rr != cudaSuccess) {                                                                            \
+                cudaEventDestroy(ev[0]);                                                                             \
+                cudaEventDestroy(ev[1]);                                                                             \
+                return e ? e : (int) rr;                                                                             \
+            }                                                                                                        \
+        }                                                                                                            \
+        int e = gpub_nullspace_projector_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, P, sP, batch);              \
+        {                                                                                                            \
+            GPUB_ENTER(ctx, sidx);                                                                                   \
+            const cudaError_t w = cudaStreamWaitEvent(stream, ev[1], 0);                                             \
+            cudaEventDestroy(ev[0]);                                                                                 \
+            cudaEventDestroy(ev[1]);                                                                                 \
+            if (w != cudaSuccess) return (int) w;                                                                    \
+        }                                                                                                            \
+        return e;                                                                                                    \
+    }
+GPUB_DEF_NSBUILD(f64, double)
+GPUB_DEF_NSBUILD(f32, float)
 
 } // extern "C"

@@ -184,6 +184,18 @@ int gpub_d2h(gpub_ctx_t ctx, cudaStream_t stream, void *dst, const void *src, si
     return GPUB_OK;
 }
 
+int gpub_ctx_fork(gpub_ctx_t ctx, cudaStream_t *side, cudaEvent_t ev[2]) {
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        if (!ctx->aux[0]) GPUB_CUDA(cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking));
+        *side = ctx->aux[0];
+    }
+    GPUB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    cudaError_t e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaEventDestroy(ev[0]); return (int) e; }
+    return GPUB_OK;
+}
+
 int gpub_ctx_aux(gpub_ctx_t ctx, cudaStream_t *up, cudaStream_t *down, size_t n_events, cudaEvent_t **events) {
     for (int i = 0; i < 2; i++)
         if (!ctx->aux[i]) GPUB_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));

@@ -312,6 +312,7 @@ template<typename T> struct Abi;
         static constexpr auto nullspace_pack = gpub_nullspace_pack_batched_##SUF;                                   \
         static constexpr auto aat = gpub_aat_batched_##SUF;                                                         \
         static constexpr auto projector = gpub_nullspace_projector_batched_##SUF;                                   \
+        static constexpr auto nullspace_build = gpub_nullspace_build_batched_##SUF;                                \
         static constexpr auto chol_from_host = gpub_chol_solve_from_host_##SUF;                                     \
     };
 GPUB200_ABI(float, f32)

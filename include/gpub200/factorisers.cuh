@@ -332,12 +332,10 @@ inline Nullspace<T>::Nullspace(DTensor<T> &a) {
     DTensor<unsigned int> const &devRank = svd.rank();
     std::shared_ptr<DTensor<T> > U = svd.leftSingularVectors().value();
     const int s = (int) aTranspose.streamIdx();
-    /* N_i = last (n - rank_i) columns of U_i, moved to the front, zero elsewhere; then N_i N_i' */
-    gpuErrChk(gpub200::Abi<T>::nullspace_pack(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(),
-                                              n * n, nMats));
-    /* N N' = I - U1 U1': the side with fewer columns is multiplied out, per matrix */
-    gpuErrChk(gpub200::Abi<T>::projector(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(), n * n,
-                                         m_projOp->raw(), n * n, nMats));
+    /* N_i = last (n - rank_i) columns of U_i, moved to the front, zero elsewhere; N_i N_i' = I - U1 U1' with the side that has
+     * fewer columns multiplied out, per matrix. One call: the packing runs beside the projector on a private stream */
+    gpuErrChk(gpub200::Abi<T>::nullspace_build(gpub200::ctx(), s, n, U->raw(), n * n, devRank.raw(), m_nullspace->raw(), n * n,
+                                               m_projOp->raw(), n * n, nMats));
     /* U and the rank tensor die with `svd` at scope exit: wait for the two launches that read them */
     Session::getInstance().synchronizeStream(aTranspose.streamIdx());
 }

@@ -281,6 +281,14 @@ int gpub_nullspace_projector_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, con
                                          const unsigned int *rank, const float *N, size_t strideN,
                                          float *P, size_t strideP, size_t batch);
 
+/* Both of the above in one call (Nullspace's constructor, tensor.cuh:2058-2079): N_i = [ U_i(:, rank_i:n) | 0 ] and P_i = N_i N_i^T.
+ * The packing (a copy) runs on a private stream beside the projector (a contraction that reads U, not N); the call's stream waits
+ * for both. */
+int gpub_nullspace_build_batched_f64(gpub_ctx_t ctx, int sidx, size_t n, const double *U, size_t strideU, const unsigned int *rank,
+                                     double *N, size_t strideN, double *P, size_t strideP, size_t batch);
+int gpub_nullspace_build_batched_f32(gpub_ctx_t ctx, int sidx, size_t n, const float *U, size_t strideU, const unsigned int *rank,
+                                     float *N, size_t strideN, float *P, size_t strideP, size_t batch);
+
 /* ---- synthetic data (bench / tests): counter-based generator, SURVEY 8(d) ---
  * x[i] = lo + (hi - lo) * u(seed, i),  u in [0,1) from a 64-bit hash of i     */
 int gpub_fill_uniform_f64(gpub_ctx_t ctx, int sidx, size_t n, double *x, double lo, double hi, uint64_t seed);

@@ -184,8 +184,7 @@ def main():
                      capi._p(work), ws, capi._p(info), batch)
             rank.zero_()
             ctx.call("count_gt_batched", S, capi._p(S), m, m, 1e-6, capi._p(rank), batch)
-            ctx.call("nullspace_pack_batched", U, n, capi._p(U), n * n, capi._p(rank), capi._p(N), n * n, batch)
-            ctx.call("nullspace_projector_batched", N, n, capi._p(U), n * n, capi._p(rank), capi._p(N), n * n, capi._p(P), n * n, batch)
+            ctx.call("nullspace_build_batched", U, n, capi._p(U), n * n, capi._p(rank), capi._p(N), n * n, capi._p(P), n * n, batch)
         med, best = timeit(build, lambda: None, max(2, args.reps // 3))
         assert int(info.abs().max()) == 0
         report("nullspace", [m, n], dt, batch, med, best, (m * n + 2 * n * n) * s, 4 * n * n * m + 22 * m ** 3 + 2 * n ** 3, rb)

@@ -395,12 +395,40 @@ def test_nullspace_projector_from_the_orthogonal_factor(gpu_ctx, dt, n):
     dN = torch.empty_like(dU); dP = torch.full_like(dU, float("nan")); dP2 = torch.empty_like(dU)
     gpu_ctx.call("nullspace_pack_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, batch)
     gpu_ctx.call("nullspace_projector_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, capi._p(dP), n * n, batch)
+    if dt == np.float64 and n % 64 == 0:
+        # tensor-pipe path: both sides are read from U itself, the packed basis is not an input (gpub_nullspace_build packs beside it)
+        dP3 = torch.empty_like(dU)
+        gpu_ctx.call("nullspace_projector_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(torch.full_like(dU, float("nan"))), n * n,
+                     capi._p(dP3), n * n, batch)
+        assert torch.equal(dP3, dP)
     gpu_ctx.call("aat_batched", dU, n, capi._p(dN), n * n, capi._p(dP2), n * n, batch)
     P, P2, N = host(dP).astype(np.float64), host(dP2).astype(np.float64), host(dN).astype(np.float64)
     tol = 20 * TOL[np.dtype(dt)]
     assert np.abs(P - N @ N.transpose(0, 2, 1)).max() <= tol and np.abs(P - P2).max() <= tol
     assert np.array_equal(P, P.transpose(0, 2, 1))
     assert np.abs(P[0] - np.eye(n)).max() <= tol and np.abs(P[7]).max() <= tol     # rank 0: identity; full rank: zero
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n", [5, 64, 128])
+def test_nullspace_build_equals_pack_then_projector(gpu_ctx, dt, n):
+    """gpub_nullspace_build_batched (the packing beside the projector on a private stream, joined on the call's stream) gives the
+    packed basis and the projector of the two separate calls, bit for bit, and work queued behind it on the call's stream sees both."""
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(3 * n)
+    ranks = np.array([0, 1, n // 2, n // 2 + 1, n - 1, n, 3 % n, n - 2], dtype=np.int32)
+    batch = len(ranks)
+    U = np.linalg.qr(rng.uniform(-1, 1, (batch, n, n)))[0].astype(dt)
+    dU = dev(U); dr = torch.from_numpy(ranks).cuda()
+    dN = torch.empty_like(dU); dP = torch.empty_like(dU)
+    gpu_ctx.call("nullspace_pack_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, batch)
+    gpu_ctx.call("nullspace_projector_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN), n * n, capi._p(dP), n * n, batch)
+    for rep in range(3):
+        dN2 = torch.full_like(dU, float("nan")); dP2 = torch.full_like(dU, float("nan"))
+        gpu_ctx.call("nullspace_build_batched", dU, n, capi._p(dU), n * n, capi._p(dr), capi._p(dN2), n * n, capi._p(dP2), n * n, batch)
+        s = dN2.sum() + dP2.sum()                  # queued on the same (current) stream right behind the call
+        assert torch.equal(dN2, dN) and torch.equal(dP2, dP) and bool(torch.isfinite(s))
 
 
 def test_nrm2_of_extreme_range_data_is_rescued_by_the_scaled_pass(gpu_ctx):
