@@ -1234,36 +1234,22 @@ GPUB_DEF_PROJ(f32, float)
             const int e = gpub_nullspace_pack_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, batch);                \
             return e ? e : gpub_nullspace_projector_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, P, sP, batch);   \
         }                                                                                                            \
+        GPUB_ENTER(ctx, sidx);                                                                                       \
         cudaStream_t side = nullptr;                                                                                 \
         cudaEvent_t ev[2] = {nullptr, nullptr};                                                                      \
-        {                                                                                                            \
-            GPUB_ENTER(ctx, sidx);                                                                                   \
-            int e = gpub_ctx_fork(ctx, &side, ev);                                                                   \
-            if (e) return e;                                                                                         \
-            cudaError_t fk = cudaEventRecord(ev[0], stream);                                                         \
-            if (fk == cudaSuccess) fk = cudaStreamWaitEvent(side, ev[0], 0);                                         \
-            if (fk != cudaSuccess) {                                                                                 \
-                cudaEventDestroy(ev[0]);                                                                             \
-                cudaEventDestroy(ev[1]);                                                                             \
-                return (int) fk;                                                                                     \
-            }                                                                                                        \
-            e = gpub_internal_nullspace_pack_##SUF(ctx, side, n, U, sU, rank, N, sN, batch);                         \
-            const cudaError_t rr = cudaEventRecord(ev[1], side);                                                     \
-            if (e || rr != cudaSuccess) {                                                                            \
-                cudaEventDestroy(ev[0]);                                                                             \
-                cudaEventDestroy(ev[1]);                                                                             \
-                return e ? e : (int) rr;                                                                             \
-            }                                                                                                        \
-        }                                                                                                            \
-        int e = gpub_nullspace_projector_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, P, sP, batch);              \
-        {                                                                                                            \
-            GPUB_ENTER(ctx, sidx);                                                                                   \
-            const cudaError_t w = cudaStreamWaitEvent(stream, ev[1], 0);                                             \
-            cudaEventDestroy(ev[0]);                                                                                 \
-            cudaEventDestroy(ev[1]);                                                                                 \
-            if (w != cudaSuccess) return (int) w;                                                                    \
-        }                                                                                                            \
-        return e;                                                                                                    \
+        int e = gpub_ctx_fork(ctx, &side, ev);                                                                       \
+        if (e) return e;                                                                                             \
+        /* the projector is launched FIRST: its persistent CTAs (six per SM, limited by shared memory) leave room for two CTAs */ \
+        /* of the copy, which then streams beside it; launched first, the copy's 16 k CTAs would fill the GPU on their own */    \
+        cudaError_t c = cudaEventRecord(ev[0], stream);                                                              \
+        if (c == cudaSuccess) c = cudaStreamWaitEvent(side, ev[0], 0);                                               \
+        if (c == cudaSuccess) e = gpub_nullspace_projector_batched_##SUF(ctx, sidx, n, U, sU, rank, N, sN, P, sP, batch); \
+        if (c == cudaSuccess && !e) e = gpub_internal_nullspace_pack_##SUF(ctx, side, n, U, sU, rank, N, sN, batch);  \
+        if (c == cudaSuccess) c = cudaEventRecord(ev[1], side);                                                      \
+        if (c == cudaSuccess) c = cudaStreamWaitEvent(stream, ev[1], 0);                                             \
+        cudaEventDestroy(ev[0]);                                                                                     \
+        cudaEventDestroy(ev[1]);                                                                                     \
+        return e ? e : (int) c;                                                                                      \
     }
 GPUB_DEF_NSBUILD(f64, double)
 GPUB_DEF_NSBUILD(f32, float)
