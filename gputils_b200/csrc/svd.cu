@@ -701,27 +701,40 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
         const long long st0 = clock64();
 #endif
         int sweep = 0;
+        // Which warp rotates which pair of half-blocks is free, so a warp FOLLOWS its first half-block (A) along the top row of the
+        // circle schedule and keeps it in registers -- columns and norms -- for as long as it stays there (NW - 1 block-rounds); only
+        // the second half-block (B) goes through shared memory every block-round. In block-round br the top row holds the items
+        // br + 1 .. br + NW - 1 (mod NH - 1); the item that reaches the head (br + 1) is handed to warp 0, which pairs it with the
+        // fixed item NH - 1, and its warp picks up the item that enters at the tail (br + NW). Half the shared-memory traffic.
+        constexpr int M = NH - 1;
+        int ja = warp;                                      // warp >= 1: the item it follows (block-round 0: item w pairs with item -w)
+        bool load_a = true;
+        T c[8][JE];
+        T nA = T(0), nB;
         for (; sweep < 40; sweep++) {
             unsigned flags = 0;
-            for (int br = 0; br < NH - 1; br++) {
-                // circle method over the half-blocks: warp 0 keeps half-block NH - 1, the others meet (br + w, br - w) mod (NH - 1)
+            for (int br = 0; br < M; br++) {
                 int ha, hb;
-                if (warp == 0) { ha = NH - 1; hb = br; }
+                if (warp == 0) { ha = M; hb = br; }
                 else {
-                    ha = br + warp; ha -= ha >= NH - 1 ? NH - 1 : 0;
-                    hb = br - warp; hb += hb < 0 ? NH - 1 : 0;
+                    ha = ja;
+                    hb = 2 * br - ja; hb += hb < 0 ? M : 0; hb -= hb >= M ? M : 0;
                 }
-                T c[8][JE];
                 T *xa = X + (size_t) (4 * ha) * ldx + lane, *xb = X + (size_t) (4 * hb) * ldx + lane;
+                if (load_a) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+#pragma unroll
+                        for (int e = 0; e < JE; e++) c[v][e] = xa[(size_t) v * ldx + 32 * e];
+                    }
+                    nA = s_sig[4 * ha + (lane & 3)];        // (ignored in block-round 0, where the norms are recomputed)
+                    load_a = false;
+                }
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
 #pragma unroll
-                    for (int e = 0; e < JE; e++) {
-                        c[v][e] = xa[(size_t) v * ldx + 32 * e];
-                        c[4 + v][e] = xb[(size_t) v * ldx + 32 * e];
-                    }
+                    for (int e = 0; e < JE; e++) c[4 + v][e] = xb[(size_t) v * ldx + 32 * e];
                 }
-                T nA, nB;
                 bool dirty = false;
                 if (br == 0) {
                     // first block-round of a sweep: exact norms, then the pairs inside each half-block (three rounds, norms held by every lane)
@@ -738,7 +751,6 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                     dirty = true;
                 } else {
                     // the squared norms travel with the columns (s_sig is free until the tail)
-                    nA = s_sig[4 * ha + (lane & 3)];
                     nB = s_sig[4 * hb + (lane & 3)];
                 }
                 jblk_cross<T, JE, 0>(c, nA, nB, lane, tol2, quad2, flags, dirty);
@@ -751,18 +763,30 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
                     nA = __shfl_sync(0xffffffffu, tot, 4 * (lane & 3));
                     nB = __shfl_sync(0xffffffffu, tot, 16 + 4 * (lane & 3));
                 }
+                // A goes back to shared memory when another warp takes it over next (its item reaches the head of the top row)
+                // and at the end of a sweep (the tail reads every column from shared memory)
+                const int nbr = br + 1 == M ? 0 : br + 1;
+                const bool hand_over = warp != 0 && ja == nbr;
                 __syncwarp();                               // every lane has read the norms lanes 0..3 are about to replace
                 if (lane < 4) {
-                    s_sig[4 * ha + lane] = nA;
                     s_sig[4 * hb + lane] = nB;
+                    if (hand_over || br == M - 1) s_sig[4 * ha + lane] = nA;
                 }
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
 #pragma unroll
-                    for (int e = 0; e < JE; e++) {
-                        xa[(size_t) v * ldx + 32 * e] = c[v][e];
-                        xb[(size_t) v * ldx + 32 * e] = c[4 + v][e];
+                    for (int e = 0; e < JE; e++) xb[(size_t) v * ldx + 32 * e] = c[4 + v][e];
+                }
+                if (hand_over || br == M - 1) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+#pragma unroll
+                        for (int e = 0; e < JE; e++) xa[(size_t) v * ldx + 32 * e] = c[v][e];
                     }
+                }
+                if (hand_over) {
+                    ja = br + NW; ja -= ja >= M ? M : 0;    // the item that enters the top row at its tail
+                    load_a = true;
                 }
                 __syncthreads();
             }
