@@ -593,7 +593,8 @@ __device__ __forceinline__ void jblk_cross(T (&c)[8][JE], T &nA, T &nB, int lane
     const unsigned rmask = __ballot_sync(0xffffffffu, rot) & 0xfu;
     flags |= rot ? ((!(c2 <= quad2 * ab) || tt > quad2) ? 3u : 1u) : 0u;
     // a norm that lost more than a decimal digit to cancellation is recomputed from the column at the end of the block-round
-    dirty = dirty || !(nA - dl > T(0.0625) * nA) || !(nB + dl > T(0.0625) * nB);
+    // (the transfer t c shrinks the smaller of the two norms: that is the one that can cancel)
+    dirty = dirty || !(fabs(dl) < T(0.9375) * (dl > T(0) ? nA : nB));
     nA -= dl;
     nB += dl;
     if (rmask) {
