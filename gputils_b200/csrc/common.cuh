@@ -25,11 +25,16 @@ struct gpub_stream_slot {
 #define GPUB_RING_SLOTS 4
 #define GPUB_RING_CHUNK_BYTES (8ull << 20)
 
+// stream slots from this index on are the library's own: side streams for work that can run beside the caller's stream
+// (chunks of a batched SVD); gpub_ctx_num_streams does not count them
+constexpr int GPUB_INTERNAL_SLOT0 = 4064;
+
 struct gpub_ctx {
     int device = 0;
     int sm_count = 148;
     int max_smem_optin = 0;
     std::deque<gpub_stream_slot> slots;  // deque: growing never moves existing slots
+    size_t user_slots = 0;               // slots below GPUB_INTERNAL_SLOT0 in use (the library's own side streams live above it)
     std::mutex mu;
     // stream-ordered allocator behind Session::cudaAllocate (gpub_mem_alloc / gpub_mem_free): a context-owned pool whose
     // release threshold keeps freed blocks cached, so a DTensor constructor / destructor is a pool hit, not a cudaMalloc

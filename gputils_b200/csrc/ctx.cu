@@ -13,10 +13,15 @@ namespace {
 std::mutex g_registry_mu;
 std::map<int, std::unique_ptr<gpub_ctx>> g_registry;
 
-int init_slot(gpub_stream_slot &s, cudaStream_t external) {
+int init_slot(gpub_stream_slot &s, cudaStream_t external, bool internal = false) {
     if (external) {
         s.stream = external;
         s.owned = false;
+    } else if (internal) {
+        // the library's own side streams: ordered against the caller's stream by events only (a blocking stream would also order
+        // against every legacy-stream operation in between, which serialises the chunks when the caller's stream IS the legacy stream)
+        GPUB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        s.owned = true;
     } else {
         // blocking stream, like the reference's cudaStreamCreate (tensor.cuh:161): legacy
         // default-stream work and synchronous cudaMemcpy order against it.
@@ -40,9 +45,10 @@ gpub_stream_slot *gpub_slot(gpub_ctx_t ctx, int sidx, int *err) {
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
     if ((size_t) sidx >= ctx->slots.size()) ctx->slots.resize(sidx + 1);
+    if (sidx < GPUB_INTERNAL_SLOT0 && (size_t) sidx + 1 > ctx->user_slots) ctx->user_slots = (size_t) sidx + 1;
     gpub_stream_slot &s = ctx->slots[sidx];
     if (!s.stream) {
-        int e = init_slot(s, nullptr);
+        int e = init_slot(s, nullptr, sidx >= GPUB_INTERNAL_SLOT0);
         if (e != GPUB_OK) {
             *err = e;
             return nullptr;
@@ -106,7 +112,7 @@ int gpub_ctx_ensure_streams(gpub_ctx_t ctx, int n) {
 int gpub_ctx_num_streams(gpub_ctx_t ctx) {
     if (!ctx) return 0;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    return (int) ctx->slots.size();
+    return (int) ctx->user_slots;
 }
 
 int gpub_ctx_stream(gpub_ctx_t ctx, int sidx, void **cuda_stream) {
@@ -121,6 +127,7 @@ int gpub_ctx_bind_stream(gpub_ctx_t ctx, int sidx, void *cuda_stream) {
     gpub_device_guard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->mu);
     if ((size_t) sidx >= ctx->slots.size()) ctx->slots.resize(sidx + 1);
+    if (sidx < GPUB_INTERNAL_SLOT0 && (size_t) sidx + 1 > ctx->user_slots) ctx->user_slots = (size_t) sidx + 1;
     gpub_stream_slot &s = ctx->slots[sidx];
     if (s.stream && s.owned) {
         GPUB_CUDA(cudaStreamSynchronize(s.stream));

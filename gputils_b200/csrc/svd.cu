@@ -984,6 +984,10 @@ inline bool shape_supported(size_t m, size_t n) {
     return n <= 256 && jacobi_smem<T>(n) <= (size_t) 227 * 1024 - 2048;
 }
 
+#ifndef GPUB_SVD_CHUNKS
+#define GPUB_SVD_CHUNKS 4
+#endif
+
 // 0 = shape not served by the batched kernels (the header turns that into std::invalid_argument in the Svd constructor)
 template<typename T>
 size_t worksize(size_t m, size_t n, int jobu, size_t batch) {
@@ -1005,6 +1009,40 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
     GPUB_ENTER(ctx, sidx);
     T *w = reinterpret_cast<T *>((((uintptr_t) work) + 15) & ~(uintptr_t) 15);
     const size_t per = per_matrix_work_elems(n);
+#if GPUB_SVD_CHUNKS > 1
+    if (n > 32 && sidx < GPUB_INTERNAL_SLOT0 && batch > (size_t) ctx->sm_count && batch >= 2 * GPUB_SVD_CHUNKS) {
+        // The QR and the Jacobi kernel both run one CTA per matrix and SM: a batch that is not a multiple of the SM count leaves SMs idle
+        // in the last wave of each of them (256 matrices on 148 SMs: 40 idle for half of both kernels), and every stage waits for the
+        // slowest CTA of the one before. Cut into chunks that run the whole sequence on the library's own side streams, the stages of
+        // different chunks overlap: a finished QR CTA makes room for a Jacobi CTA of another chunk, and the GEMMs of the U assembly
+        // fill the SMs the last Jacobi wave leaves idle. The chunks are separate sub-batches (own slice of every operand and of the
+        // workspace); the caller's stream forks into them and joins them again.
+        const bool wy = want_u && use_wy_assembly<T>(m, n);
+        const size_t per_all = per + (wy ? wy_extra_elems(m, n) : 0);
+        cudaEvent_t ev[GPUB_SVD_CHUNKS + 1];
+        int made = 0, e = GPUB_OK;
+        cudaError_t c = cudaSuccess;
+        for (; made <= GPUB_SVD_CHUNKS && c == cudaSuccess; made++) c = cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming);
+        if (c != cudaSuccess) made--;
+        if (c == cudaSuccess) c = cudaEventRecord(ev[GPUB_SVD_CHUNKS], stream);
+        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) {
+            const size_t lo = ch * batch / GPUB_SVD_CHUNKS, hi = (ch + 1) * batch / GPUB_SVD_CHUNKS;
+            int serr = 0;
+            gpub_stream_slot *side = gpub_slot(ctx, GPUB_INTERNAL_SLOT0 + ch, &serr);
+            if (!side) { e = serr; break; }
+            c = cudaStreamWaitEvent(side->stream, ev[GPUB_SVD_CHUNKS], 0);
+            if (c != cudaSuccess) break;
+            e = gesvd_batched<T>(ctx, GPUB_INTERNAL_SLOT0 + ch, jobu, m, n, A + lo * sA, lda, sA, S + lo * sS, sS, U ? U + lo * sU : nullptr, ldu, sU,
+                                 Vt + lo * sVt, ldvt, sVt, w + per_all * lo, per_all * (hi - lo) * sizeof(T) + 256 /* aligned already: the slack is not touched */,
+                                 info ? info + lo : nullptr, hi - lo);
+            if (!e) c = cudaEventRecord(ev[ch], side->stream);
+        }
+        // (the joins come after ALL the launches: on a legacy default stream each of them is a device-wide ordering point)
+        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) c = cudaStreamWaitEvent(stream, ev[ch], 0);
+        for (int i = 0; i < made; i++) cudaEventDestroy(ev[i]);
+        return e ? e : (int) c;
+    }
+#endif
 
     if (m <= 64 && n <= 32) {
         const unsigned grid = (unsigned) gpub_ceil_div(batch, 64);
