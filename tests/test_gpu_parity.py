@@ -231,6 +231,30 @@ def test_gesvd_rank_deficient_factors_stay_orthogonal(gpu_ctx, oracle, dt, m, n)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n,want_u", [(64, 64, True), (128, 64, False), (192, 96, True)])
+def test_gesvd_chunked_batch_equals_small_batches(gpu_ctx, dt, m, n, want_u):
+    """A batch larger than the SM count is cut into sub-batches that run on the library's side streams (gesvd_batched): every
+    matrix must get exactly what it gets in a batch small enough to run as one piece -- same kernels per matrix, so bit for bit --
+    which pins the slicing of every operand and of the workspace, the fork and the join."""
+    import torch
+    from gputils_b200 import capi
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    batch = 2 * sms + 7
+    rng = np.random.default_rng(5 * m + n)
+    A = rng.uniform(-1, 1, (batch, m, n)).astype(dt)
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), want_u)
+    nxt = (S.sum() + Vt.sum()).item()                    # queued behind the call on the same stream: must see every chunk
+    assert np.isfinite(nxt) and not info.cpu().numpy().any()
+    step = sms // 2
+    for lo in range(0, batch, step):
+        hi = min(batch, lo + step)
+        S1, U1, Vt1, info1 = capi.gesvd_batched(gpu_ctx, dev(A[lo:hi]), want_u)
+        assert torch.equal(S[lo:hi], S1) and torch.equal(Vt[lo:hi], Vt1) and not info1.cpu().numpy().any()
+        if want_u:
+            assert torch.equal(U[lo:hi], U1)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("m,n", [(128, 64), (256, 128)])
 def test_gesvd_clustered_singular_values(gpu_ctx, dt, m, n):
     """Multiple singular values (half of them 2, half 1, and the identity-like case of all equal): between columns of equal norm a
