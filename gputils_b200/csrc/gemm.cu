@@ -1172,7 +1172,7 @@ bool try_projector_dmma<double>(gpub_ctx_t ctx, cudaStream_t stream, size_t n, c
     if (!projector_reads_u_only<double>(n, U, sU)) return false;
     const size_t tm = n / 64, total = tm * (tm + 1) / 2 * batch, cap = (size_t) ctx->sm_count * 8;
     constexpr size_t smemT = sizeof(double) * (2 * 16 * DLD + 2 * 16 * DLD);
-    k_gemm_dmma<true, 16, 8, true, true><<<(unsigned) (total < cap ? total : cap), 256, smemT, stream>>>(n, n, n, 1.0, U, n, sU, U, n, sU, 0.0, P, n, sP,
+    k_gemm_dmma<true, 16, 4, true, true><<<(unsigned) (total < cap ? total : cap), 128, smemT, stream>>>(n, n, n, 1.0, U, n, sU, U, n, sU, 0.0, P, n, sP,
                                                                                                          tm, tm, batch, rank, U, sU);
     return true;
 }
