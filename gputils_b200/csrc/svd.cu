@@ -190,8 +190,8 @@ constexpr int JP = GPUB_JACOBI_PAIRS;   // pairs a warp rotates at once (4 or 2)
 constexpr int JRP = JP == 4 ? 16 : 8;   // values in the transpose-reduce (3 per pair, padded to a power of two)
 
 template<typename T> struct JacobiEps;
-template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; };
-template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; static constexpr float big = 1e15f; };
+template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; static constexpr double huge = 1.7e308; };
+template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; static constexpr float big = 1e15f; static constexpr float huge = 3.4e38f; };
 
 // reciprocal square root / reciprocal from the MUFU seed plus Newton steps (~1 ulp, no slow-path call)
 template<typename T> __device__ __forceinline__ T jac_rsqrt(T x);
@@ -233,12 +233,49 @@ __device__ __forceinline__ T jwarp_sum(T v) {
     return v;
 }
 
+// X = (R / 2^e)' into shared memory, 2^e the power of two that brings the largest entry of R into [1/2, 1): the rotations work with
+// squared column norms and their products (fourth powers of the entries), which leave the exponent range long before the entries do
+// (LAPACK's gesvd scales for the same reason). The scaling is exact; the singular values are multiplied back by 2^e at the end.
+// Returns 2^e. s_red: NT / 32 values of scratch. Ends with a CTA barrier.
+template<typename T, int NT>
+__device__ __forceinline__ T jacobi_load_scaled(int n, int ldx, const T *__restrict__ a_g, size_t lda, T *X, T *s_red) {
+    const int tid = threadIdx.x;
+    T amax = T(0);
+    for (int e = tid; e < n * n; e += NT) {
+        const int p = e / n, r = e % n;                  // X(r, p) = R(p, r)
+        const T v = (p <= r) ? a_g[p + (size_t) r * lda] : T(0);
+        X[(size_t) p * ldx + r] = v;
+        const T av = fabs(v);
+        amax = (av > amax && av <= JacobiEps<T>::huge) ? av : amax;   // (NaN / inf entries do not take part)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T other = __shfl_xor_sync(0xffffffffu, amax, o);
+        amax = other > amax ? other : amax;
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5] = amax;
+    __syncthreads();
+    amax = s_red[0];
+    for (int w = 1; w < NT / 32; w++) amax = s_red[w] > amax ? s_red[w] : amax;
+    int ex = 0;
+    if (amax > T(0)) (void) frexp(amax, &ex);
+    const T down = ldexp(T(1), -ex), up = ldexp(T(1), ex);
+    if (ex != 0) {
+        for (int e = tid; e < n * n; e += NT) {
+            const int p = e / n, r = e % n;
+            if (p <= r) X[(size_t) p * ldx + r] *= down;
+        }
+    }
+    __syncthreads();
+    return up;
+}
+
 // Tail of the Jacobi kernels: X (shared memory, column p at X + p * ldx) holds the orthogonalised columns W D. Singular values = column
 // norms, sorted descending; Vt rows = normalised columns; columns without a singular value (rank deficiency) are replaced by an
 // orthonormal completion so that Vt is always orthogonal (Nullspace relies on it). NT = threads of the CTA.
 template<typename T, int NT>
 __device__ __forceinline__ void jacobi_finish(int n, int ldx, T *X, T *s_sig, T *s_coef, int *s_perm, T *s_val, int *s_idx, T *s_g, T *vt_g,
-                                              size_t ldvt, T *J, int want_u) {
+                                              size_t ldvt, T *J, int want_u, T unscale) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NW = NT / 32;
     constexpr int JT = NT;
@@ -261,7 +298,7 @@ __device__ __forceinline__ void jacobi_finish(int n, int ldx, T *X, T *s_sig, T 
         s_perm[rank] = p;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += JT) s_g[i] = s_sig[s_perm[i]];
+    for (int i = tid; i < n; i += JT) s_g[i] = s_sig[s_perm[i]] * unscale;
     const T smax = s_sig[s_perm[0]];
     const T thr = smax * (T) n * (T) JacobiEps<T>::v;
     // normalise the columns that carry a singular value; count them
@@ -370,12 +407,10 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         const T *a_g = A + mat * sA;
         T *J = want_u ? Ur + mat * sUr : nullptr;
-        for (int e = tid; e < n * n; e += JT) {
-            const int p = e / n, r = e % n;              // X(r, p) = R(p, r)
-            X[(size_t) p * ldx + r] = (p <= r) ? a_g[p + (size_t) r * lda] : T(0);
-            if (want_u) J[e] = (p == r) ? T(1) : T(0);   // J(r, p) at J[r + p*n]; identity is symmetric
+        if (want_u) {
+            for (int e = tid; e < n * n; e += JT) J[e] = (e / n == e % n) ? T(1) : T(0);   // J(r, p) at J[r + p*n]
         }
-        __syncthreads();
+        const T unscale = jacobi_load_scaled<T, JT>(n, ldx, a_g, lda, X, s_val);
         int sweep = 0;
         for (; sweep < 40; sweep++) {
             if (tid == 0) s_rot = 0;
@@ -476,7 +511,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
             if (s_rot == 0) break;
             __syncthreads();
         }
-        jacobi_finish<T, JT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, J, want_u);
+        jacobi_finish<T, JT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, J, want_u, unscale);
         if (tid == 0 && info) info[mat] = sweep >= 40 ? 1 : 0;
         __syncthreads();
     }
@@ -692,12 +727,8 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
 
     for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
         const T *a_g = A + mat * sA;
-        for (int e = tid; e < n * n; e += NT) {
-            const int p = e / n, r = e % n;              // X(r, p) = R(p, r)
-            X[(size_t) p * ldx + r] = (p <= r) ? a_g[p + (size_t) r * lda] : T(0);
-        }
         if (tid == 0) s_flags = 0;
-        __syncthreads();
+        const T unscale = jacobi_load_scaled<T, NT>(n, ldx, a_g, lda, X, s_val);
 #ifdef GPUB_JBLK_STATS
         const long long st0 = clock64();
 #endif
@@ -802,7 +833,7 @@ __global__ void __launch_bounds__(128 * JE) k_jacobi_blk(const T *__restrict__ A
 #ifdef GPUB_JBLK_STATS
         const long long st1 = clock64();
 #endif
-        jacobi_finish<T, NT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, (T *) nullptr, 0);
+        jacobi_finish<T, NT>(n, ldx, X, s_sig, s_coef, s_perm, s_val, s_idx, S + mat * sS, Vt + mat * sVt, ldvt, (T *) nullptr, 0, unscale);
         if (tid == 0 && info) info[mat] = sweep >= 40 ? 1 : 0;
         __syncthreads();
 #ifdef GPUB_JBLK_STATS

@@ -230,6 +230,32 @@ def test_gesvd_rank_deficient_factors_stay_orthogonal(gpu_ctx, oracle, dt, m, n)
     assert np.abs(Un[:, :, r:].transpose(0, 2, 1) @ A.astype(np.float64)).max() <= 1e3 * tol * So.max()
 
 
+@pytest.mark.parametrize("n", [64, 128])
+def test_gesvd_graded_and_scaled_matrices(gpu_ctx, n):
+    """Singular values spread over twelve decades, and the same matrix scaled by 1e+100 / 1e-100 (the squared column norms the
+    rotations work with are then 1e+-200): values relative to the largest, orthogonality and reconstruction must not notice the scale
+    (fp64; k_jacobi_blk computes the rotation tangent in single precision after scaling the pair's quantities to order one)."""
+    from gputils_b200 import capi
+    rng = np.random.default_rng(n)
+    m = 2 * n
+    Q, _ = np.linalg.qr(rng.normal(size=(m, n))); V, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    sig = np.logspace(0, -12, n)
+    A0 = (Q * sig) @ V.T
+    A = np.stack([A0, 1e100 * A0, 1e-100 * A0, np.eye(m, n), np.zeros((m, n))])
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), True)
+    assert not info.cpu().numpy().any()
+    Sn = S.cpu().numpy(); Un = host(U); Vn = host(Vt)
+    tol = 100 * TOL[np.dtype(np.float64)]
+    for i, scale in ((0, 1.0), (1, 1e100), (2, 1e-100)):
+        assert np.abs(Sn[i] / scale - sig).max() <= 1e-13, (i, np.abs(Sn[i] / scale - sig).max())
+        assert rel_err((Un[i][:, :n] * Sn[i]) @ Vn[i], A[i]) <= tol
+    assert np.abs(Sn[1] / 1e100 - Sn[0]).max() <= 1e-13 and np.abs(Sn[2] * 1e100 - Sn[0]).max() <= 1e-13
+    assert np.abs(Sn[3] - 1.0).max() <= 1e-14 and np.abs(Sn[4]).max() == 0.0
+    for i in range(5):
+        eV, eU = np.abs(Vn[i] @ Vn[i].T - np.eye(n)).max(), np.abs(Un[i].T @ Un[i] - np.eye(m)).max()
+        assert eV <= tol and eU <= tol, (i, eV, eU)
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("m,n,want_u", [(64, 64, True), (128, 64, False), (192, 96, True)])
 def test_gesvd_chunked_batch_equals_small_batches(gpu_ctx, dt, m, n, want_u):
