@@ -1027,54 +1027,92 @@ size_t worksize(size_t m, size_t n, int jobu, size_t batch) {
     return (per_matrix_work_elems(n) + (wy ? wy_extra_elems(m, n) : 0)) * batch * sizeof(T) + 256;
 }
 
-template<typename T>
-int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, size_t lda, size_t sA, T *S, size_t sS, T *U,
-                  size_t ldu, size_t sU, T *Vt, size_t ldvt, size_t sVt, void *work, size_t work_bytes, int *info, size_t batch) {
-    if (m == 0 || n == 0 || batch == 0) return GPUB_OK;
-    const bool want_u = (jobu == 'A' || jobu == 'a');
-    if (!want_u && !(jobu == 'N' || jobu == 'n')) return GPUB_EINVAL;
-    if (!A || !S || !Vt || (want_u && !U) || !work) return GPUB_EINVAL;
-    if (m < n || lda < m || ldvt < n || (want_u && ldu < m)) return GPUB_EINVAL;
-    if (!shape_supported<T>(m, n)) return GPUB_ENOTSUP;
-    if (work_bytes < worksize<T>(m, n, jobu, batch)) return GPUB_EWORK;
-    GPUB_ENTER(ctx, sidx);
-    T *w = reinterpret_cast<T *>((((uintptr_t) work) + 15) & ~(uintptr_t) 15);
-    const size_t per = per_matrix_work_elems(n);
-#if GPUB_SVD_CHUNKS > 1
-    if (n > 32 && sidx < GPUB_INTERNAL_SLOT0 && batch > (size_t) ctx->sm_count && batch >= 2 * GPUB_SVD_CHUNKS) {
-        // The QR and the Jacobi kernel both run one CTA per matrix and SM: a batch that is not a multiple of the SM count leaves SMs idle
-        // in the last wave of each of them (256 matrices on 148 SMs: 40 idle for half of both kernels), and every stage waits for the
-        // slowest CTA of the one before. Cut into chunks that run the whole sequence on the library's own side streams, the stages of
-        // different chunks overlap: a finished QR CTA makes room for a Jacobi CTA of another chunk, and the GEMMs of the U assembly
-        // fill the SMs the last Jacobi wave leaves idle. The chunks are separate sub-batches (own slice of every operand and of the
-        // workspace); the caller's stream forks into them and joins them again.
-        const bool wy = want_u && use_wy_assembly<T>(m, n);
-        const size_t per_all = per + (wy ? wy_extra_elems(m, n) : 0);
-        cudaEvent_t ev[GPUB_SVD_CHUNKS + 1];
-        int made = 0, e = GPUB_OK;
-        cudaError_t c = cudaSuccess;
-        for (; made <= GPUB_SVD_CHUNKS && c == cudaSuccess; made++) c = cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming);
-        if (c != cudaSuccess) made--;
-        if (c == cudaSuccess) c = cudaEventRecord(ev[GPUB_SVD_CHUNKS], stream);
-        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) {
-            const size_t lo = ch * batch / GPUB_SVD_CHUNKS, hi = (ch + 1) * batch / GPUB_SVD_CHUNKS;
-            int serr = 0;
-            gpub_stream_slot *side = gpub_slot(ctx, GPUB_INTERNAL_SLOT0 + ch, &serr);
-            if (!side) { e = serr; break; }
-            c = cudaStreamWaitEvent(side->stream, ev[GPUB_SVD_CHUNKS], 0);
-            if (c != cudaSuccess) break;
-            e = gesvd_batched<T>(ctx, GPUB_INTERNAL_SLOT0 + ch, jobu, m, n, A + lo * sA, lda, sA, S + lo * sS, sS, U ? U + lo * sU : nullptr, ldu, sU,
-                                 Vt + lo * sVt, ldvt, sVt, w + per_all * lo, per_all * (hi - lo) * sizeof(T) + 256 /* aligned already: the slack is not touched */,
-                                 info ? info + lo : nullptr, hi - lo);
-            if (!e) c = cudaEventRecord(ev[ch], side->stream);
-        }
-        // (the joins come after ALL the launches: on a legacy default stream each of them is a device-wide ordering point)
-        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) c = cudaStreamWaitEvent(stream, ev[ch], 0);
-        for (int i = 0; i < made; i++) cudaEventDestroy(ev[i]);
-        return e ? e : (int) c;
-    }
-#endif
+// ------------------------------------------------------------------------------------------
+// Range guard (LAPACK's gesvd scales a matrix whose largest entry is below sqrt(safmin) / eps or above its reciprocal, dlascl): the QR
+// step and the rotations work with sums of squares, which underflow (or overflow) long before the entries do -- a matrix of
+// entries around 1e-150 with small singular values came back with U orthogonal to 1e-4 only, one of 256 x 64 with NaN. One CTA per
+// matrix finds the largest entry and, only when it is out of range, multiplies the matrix by the power of two that brings it to order
+// one (exact); the factor to multiply the singular values back by is left in the last element of the matrix's workspace slice
+// and applied by k_unscale_s at the end. In range -- always, for ordinary data -- this is one read of the batch.
+// ------------------------------------------------------------------------------------------
+template<typename T> struct VecPair;
+template<> struct VecPair<double> { using type = double2; };
+template<> struct VecPair<float> { using type = float2; };
+template<typename T> struct SvdRange;
+template<> struct SvdRange<double> { static constexpr double small = 1.35e-138, big = 7.4e137, huge = 1.7e308; };
+template<> struct SvdRange<float> { static constexpr float small = 1.8e-12f, big = 5.5e11f, huge = 3.4e38f; };
 
+template<typename T>
+__global__ void __launch_bounds__(512) k_prescale(int m, int n, T *A, size_t lda, size_t sA, T *w, size_t per, size_t batch) {
+    __shared__ T s_red[16];
+    const int tid = threadIdx.x;
+    for (size_t mat = blockIdx.x; mat < batch; mat += gridDim.x) {
+        T *a = A + mat * sA;
+        T amax = T(0);
+        if (lda == (size_t) m && ((size_t) m * n) % (2 * 512 * 8) == 0 && (((uintptr_t) a) & 15u) == 0) {
+            // dense matrix: 128-bit loads, eight per thread in flight (this pass is one read of the whole batch)
+            using V2 = typename VecPair<T>::type;
+            const V2 *a2 = reinterpret_cast<const V2 *>(a);
+            const size_t n2 = (size_t) m * n / 2;
+            for (size_t i0 = tid; i0 < n2; i0 += 512 * 8) {
+                V2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = a2[i0 + (size_t) u * 512];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const T ax = fabs(v[u].x), ay = fabs(v[u].y);
+                    amax = (ax > amax && ax <= SvdRange<T>::huge) ? ax : amax;
+                    amax = (ay > amax && ay <= SvdRange<T>::huge) ? ay : amax;
+                }
+            }
+        } else {
+            for (int j = 0; j < n; j++)
+                for (int i = tid; i < m; i += 512) {
+                    const T av = fabs(a[(size_t) j * lda + i]);
+                    amax = (av > amax && av <= SvdRange<T>::huge) ? av : amax;
+                }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T other = __shfl_xor_sync(0xffffffffu, amax, o);
+            amax = other > amax ? other : amax;
+        }
+        if ((tid & 31) == 0) s_red[tid >> 5] = amax;
+        __syncthreads();
+        amax = s_red[0];
+        for (int k = 1; k < 16; k++) amax = s_red[k] > amax ? s_red[k] : amax;
+        T up = T(1);
+        if (amax > T(0) && (amax < SvdRange<T>::small || amax > SvdRange<T>::big)) {
+            int ex = 0;
+            (void) frexp(amax, &ex);
+            // two half steps: 2^-ex itself may not be representable when the entries are near the bottom of the range
+            const T d1 = ldexp(T(1), -(ex / 2)), d2 = ldexp(T(1), -(ex - ex / 2));
+            for (int j = 0; j < n; j++)
+                for (int i = tid; i < m; i += 512) a[(size_t) j * lda + i] = (a[(size_t) j * lda + i] * d1) * d2;
+            up = T(-1);                                   // marker: the factor is 2^ex, applied in two steps as well
+            if (tid == 0) w[mat * per + per - 2] = (T) ex;
+        }
+        if (tid == 0) w[mat * per + per - 1] = up;
+        __syncthreads();
+    }
+}
+
+template<typename T>
+__global__ void k_unscale_s(int n, T *S, size_t sS, const T *__restrict__ w, size_t per, size_t batch) {
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < (size_t) n * batch; e += (size_t) gridDim.x * blockDim.x) {
+        const size_t mat = e / n;
+        if (w[mat * per + per - 1] < T(0)) {
+            const int ex = (int) w[mat * per + per - 2];
+            T *sp = S + mat * sS + (e - mat * n);
+            *sp = ldexp(ldexp(*sp, ex / 2), ex - ex / 2);
+        }
+    }
+}
+
+// the paths of gesvd_batched on one sub-batch and one stream
+template<typename T>
+int gesvd_paths(gpub_ctx_t ctx, int sidx, cudaStream_t stream, bool want_u, size_t m, size_t n, T *A, size_t lda, size_t sA, T *S, size_t sS, T *U,
+                size_t ldu, size_t sU, T *Vt, size_t ldvt, size_t sVt, T *w, size_t per, int *info, size_t batch) {
     if (m <= 64 && n <= 32) {
         const unsigned grid = (unsigned) gpub_ceil_div(batch, 64);
         k_gesvd_small<T><<<grid, 64, 0, stream>>>((int) m, (int) n, A, lda, sA, S, sS, U, ldu, sU, Vt, ldvt, sVt, w, per, want_u ? 1 : 0,
@@ -1196,6 +1234,71 @@ int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, 
         GPUB_LAUNCH_CHECK();
         e = internal_ormqr<T>(ctx, sidx, 0, m, m, n, A, lda, sA, tau, per, U, ldu, sU, batch);
         if (e) return e;
+    }
+    return GPUB_OK;
+}
+
+template<typename T>
+int gesvd_batched(gpub_ctx_t ctx, int sidx, int jobu, size_t m, size_t n, T *A, size_t lda, size_t sA, T *S, size_t sS, T *U,
+                  size_t ldu, size_t sU, T *Vt, size_t ldvt, size_t sVt, void *work, size_t work_bytes, int *info, size_t batch) {
+    if (m == 0 || n == 0 || batch == 0) return GPUB_OK;
+    const bool want_u = (jobu == 'A' || jobu == 'a');
+    if (!want_u && !(jobu == 'N' || jobu == 'n')) return GPUB_EINVAL;
+    if (!A || !S || !Vt || (want_u && !U) || !work) return GPUB_EINVAL;
+    if (m < n || lda < m || ldvt < n || (want_u && ldu < m)) return GPUB_EINVAL;
+    if (!shape_supported<T>(m, n)) return GPUB_ENOTSUP;
+    if (work_bytes < worksize<T>(m, n, jobu, batch)) return GPUB_EWORK;
+    GPUB_ENTER(ctx, sidx);
+    T *w = reinterpret_cast<T *>((((uintptr_t) work) + 15) & ~(uintptr_t) 15);
+    const size_t per = per_matrix_work_elems(n);
+#if GPUB_SVD_CHUNKS > 1
+    if (n > 32 && sidx < GPUB_INTERNAL_SLOT0 && batch > (size_t) ctx->sm_count && batch >= 2 * GPUB_SVD_CHUNKS) {
+        // The QR and the Jacobi kernel both run one CTA per matrix and SM: a batch that is not a multiple of the SM count leaves SMs idle
+        // in the last wave of each of them (256 matrices on 148 SMs: 40 idle for half of both kernels), and every stage waits for the
+        // slowest CTA of the one before. Cut into chunks that run the whole sequence on the library's own side streams, the stages of
+        // different chunks overlap: a finished QR CTA makes room for a Jacobi CTA of another chunk, and the GEMMs of the U assembly
+        // fill the SMs the last Jacobi wave leaves idle. The chunks are separate sub-batches (own slice of every operand and of the
+        // workspace); the caller's stream forks into them and joins them again.
+        const bool wy = want_u && use_wy_assembly<T>(m, n);
+        const size_t per_all = per + (wy ? wy_extra_elems(m, n) : 0);
+        cudaEvent_t ev[GPUB_SVD_CHUNKS + 1];
+        int made = 0, e = GPUB_OK;
+        cudaError_t c = cudaSuccess;
+        for (; made <= GPUB_SVD_CHUNKS && c == cudaSuccess; made++) c = cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming);
+        if (c != cudaSuccess) made--;
+        if (c == cudaSuccess) c = cudaEventRecord(ev[GPUB_SVD_CHUNKS], stream);
+        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) {
+            const size_t lo = ch * batch / GPUB_SVD_CHUNKS, hi = (ch + 1) * batch / GPUB_SVD_CHUNKS;
+            int serr = 0;
+            gpub_stream_slot *side = gpub_slot(ctx, GPUB_INTERNAL_SLOT0 + ch, &serr);
+            if (!side) { e = serr; break; }
+            c = cudaStreamWaitEvent(side->stream, ev[GPUB_SVD_CHUNKS], 0);
+            if (c != cudaSuccess) break;
+            e = gesvd_batched<T>(ctx, GPUB_INTERNAL_SLOT0 + ch, jobu, m, n, A + lo * sA, lda, sA, S + lo * sS, sS, U ? U + lo * sU : nullptr, ldu, sU,
+                                 Vt + lo * sVt, ldvt, sVt, w + per_all * lo, per_all * (hi - lo) * sizeof(T) + 256 /* aligned already: the slack is not touched */,
+                                 info ? info + lo : nullptr, hi - lo);
+            if (!e) c = cudaEventRecord(ev[ch], side->stream);
+        }
+        // (the joins come after ALL the launches: on a legacy default stream each of them is a device-wide ordering point)
+        for (int ch = 0; ch < GPUB_SVD_CHUNKS && c == cudaSuccess && !e; ch++) c = cudaStreamWaitEvent(stream, ev[ch], 0);
+        for (int i = 0; i < made; i++) cudaEventDestroy(ev[i]);
+        return e ? e : (int) c;
+    }
+#endif
+
+    if (m <= 64 && n <= 32)   // LAPACK-faithful thread-per-matrix path: scale-safe building blocks (lartg, lasv2, nrm2 with scaling)
+        return gesvd_paths<T>(ctx, sidx, stream, want_u, m, n, A, lda, sA, S, sS, U, ldu, sU, Vt, ldvt, sVt, w, per, info, batch);
+    {
+        const size_t cap = (size_t) ctx->sm_count * 4;
+        k_prescale<T><<<(unsigned) (batch < cap ? batch : cap), 512, 0, stream>>>((int) m, (int) n, A, lda, sA, w, per, batch);
+        GPUB_LAUNCH_CHECK();
+    }
+    const int e = gesvd_paths<T>(ctx, sidx, stream, want_u, m, n, A, lda, sA, S, sS, U, ldu, sU, Vt, ldvt, sVt, w, per, info, batch);
+    if (e) return e;
+    {
+        const size_t tot = gpub_ceil_div(n * batch, 256);
+        k_unscale_s<T><<<(unsigned) (tot < 1024 ? tot : 1024), 256, 0, stream>>>((int) n, S, sS, w, per, batch);
+        GPUB_LAUNCH_CHECK();
     }
     return GPUB_OK;
 }

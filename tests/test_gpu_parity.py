@@ -230,28 +230,32 @@ def test_gesvd_rank_deficient_factors_stay_orthogonal(gpu_ctx, oracle, dt, m, n)
     assert np.abs(Un[:, :, r:].transpose(0, 2, 1) @ A.astype(np.float64)).max() <= 1e3 * tol * So.max()
 
 
-@pytest.mark.parametrize("n", [64, 128])
-def test_gesvd_graded_and_scaled_matrices(gpu_ctx, n):
-    """Singular values spread over twelve decades, and the same matrix scaled by 1e+100 / 1e-100 (the squared column norms the
-    rotations work with are then 1e+-200): values relative to the largest, orthogonality and reconstruction must not notice the scale
-    (fp64; k_jacobi_blk computes the rotation tangent in single precision after scaling the pair's quantities to order one)."""
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m,n", [(128, 64), (256, 128), (200, 20), (100, 33)])
+def test_gesvd_graded_and_scaled_matrices(gpu_ctx, dt, m, n):
+    """Singular values spread over many decades, and the same matrix scaled towards both ends of the exponent range: values relative to
+    the largest, orthogonality and reconstruction must not notice the scale. Two guards are exercised: the Jacobi kernels bring the R
+    factor to order one (squared norms and their products leave the range long before the entries do), and gesvd_batched scales a
+    matrix whose largest entry is outside LAPACK's [sqrt(safmin) / eps, eps / sqrt(safmin)] before the QR step (k_prescale)."""
     from gputils_b200 import capi
-    rng = np.random.default_rng(n)
-    m = 2 * n
+    f64 = dt == np.float64
+    rng = np.random.default_rng(m + n)
     Q, _ = np.linalg.qr(rng.normal(size=(m, n))); V, _ = np.linalg.qr(rng.normal(size=(n, n)))
-    sig = np.logspace(0, -12, n)
+    sig = np.logspace(0, -12 if f64 else -4, n)
     A0 = (Q * sig) @ V.T
-    A = np.stack([A0, 1e100 * A0, 1e-100 * A0, np.eye(m, n), np.zeros((m, n))])
-    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A), True)
+    scales = (1.0, 1e100, 1e-100, 1e150, 1e-150) if f64 else (1.0, 1e10, 1e-10, 1e14, 1e-16)
+    A = np.stack([s * A0 for s in scales] + [np.eye(m, n), np.zeros((m, n))]).astype(dt)
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A.copy()), True)
     assert not info.cpu().numpy().any()
-    Sn = S.cpu().numpy(); Un = host(U); Vn = host(Vt)
-    tol = 100 * TOL[np.dtype(np.float64)]
-    for i, scale in ((0, 1.0), (1, 1e100), (2, 1e-100)):
-        assert np.abs(Sn[i] / scale - sig).max() <= 1e-13, (i, np.abs(Sn[i] / scale - sig).max())
-        assert rel_err((Un[i][:, :n] * Sn[i]) @ Vn[i], A[i]) <= tol
-    assert np.abs(Sn[1] / 1e100 - Sn[0]).max() <= 1e-13 and np.abs(Sn[2] * 1e100 - Sn[0]).max() <= 1e-13
-    assert np.abs(Sn[3] - 1.0).max() <= 1e-14 and np.abs(Sn[4]).max() == 0.0
-    for i in range(5):
+    Sn = S.cpu().numpy().astype(np.float64); Un = host(U).astype(np.float64); Vn = host(Vt).astype(np.float64)
+    tol = 100 * TOL[np.dtype(dt)]
+    for i, scale in enumerate(scales):
+        es = np.abs(Sn[i] / scale - sig).max()
+        assert es <= (1e-13 if f64 else 1e-5), (scale, es)
+        assert rel_err((Un[i][:, :n] * Sn[i]) @ Vn[i], A[i].astype(np.float64)) <= tol, scale
+    k = len(scales)
+    assert np.abs(Sn[k] - 1.0).max() <= 10 * TOL[np.dtype(dt)] and np.abs(Sn[k + 1]).max() == 0.0
+    for i in range(k + 2):
         eV, eU = np.abs(Vn[i] @ Vn[i].T - np.eye(n)).max(), np.abs(Un[i].T @ Un[i] - np.eye(m)).max()
         assert eV <= tol and eU <= tol, (i, eV, eU)
 
