@@ -47,7 +47,10 @@ __device__ __forceinline__ T cta_sum(T v, T *s_red) {
 // dlarfg on (alpha, xnorm): returns beta, writes tau and the scale 1/(alpha-beta) for x
 template<typename T>
 __device__ __forceinline__ T larfg(T alpha, T xnorm2, T *tau, T *scale) {
-    if (xnorm2 == T(0)) {
+    // a column at the bottom of the exponent range counts as already reduced, like an exact zero (squares of its entries are
+    // subnormal: tau and v would no longer make an orthogonal reflector -- 1e-5 off for the all-ones matrix, whose every column
+    // is rounding noise of the one before); what is dropped is below 1e-145 (fp64) / 1e-15 (fp32) in absolute value
+    if (xnorm2 == T(0) || !(alpha * alpha + xnorm2 >= (sizeof(T) == 8 ? T(1e-290) : T(1e-30)))) {
         *tau = T(0);
         *scale = T(0);
         return alpha;
@@ -477,7 +480,10 @@ __device__ __forceinline__ void tcq_panel_column(double (&p)[TCQ_NB][RPT], const
     const double xnorm2 = __shfl_sync(0xffffffffu, tot, 0);
     const double alpha = __shfl_sync(0xffffffffu, pv, 0);
     double tau = 0.0, scale = 0.0, beta = alpha;
-    if (xnorm2 != 0.0) {
+    // a column whose norm is at the bottom of the exponent range (rounding noise of rounding noise: every column of an all-ones matrix
+    // is 1e-16 of the one before, and the flush-to-zero seeds below turn a subnormal sum of squares into inf * 0 = NaN) counts as
+    // already reduced, like an exact zero: tau = 0. What is dropped is below 1e-145 in absolute value.
+    if (xnorm2 != 0.0 && fma(alpha, alpha, xnorm2) >= 1e-290) {
         // dlarfg without the sqrt / divide slow paths (every warp evaluates this redundantly): rsqrt and rcp seeds
         // plus Newton steps, each result corrected once more against its defining residual (< 1 ulp)
         const double ss = fma(alpha, alpha, xnorm2);
@@ -746,7 +752,7 @@ __device__ __forceinline__ void tcq_trailing_rs(TcqShared sh, double *tgt, size_
 // dlarfg from alpha and the squared norm of the entries below it, without the sqrt / divide slow paths (as tcq_panel_column)
 __device__ __forceinline__ void tcq_larfg(double alpha, double xnorm2, double &beta, double &tau, double &scale) {
     tau = 0.0; scale = 0.0; beta = alpha;
-    if (xnorm2 != 0.0) {
+    if (xnorm2 != 0.0 && fma(alpha, alpha, xnorm2) >= 1e-290) {   // (below: counts as already reduced, see tcq_panel_column)
         const double ss = fma(alpha, alpha, xnorm2);
         double rn;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(ss));
@@ -1441,7 +1447,7 @@ __global__ void __launch_bounds__(128, GPUB_GELS_MINB) k_gels_f2(float *A, size_
             const float ajj = (j & 1) ? a[j][diag_pair(j)].y : a[j][diag_pair(j)].x;
             const float alpha = __shfl_sync(0xffffffffu, ajj, gl + diag_lane(j));
             float tau = 0.f, scale = 0.f, beta = alpha;
-            if (xnorm2 != 0.f) {
+            if (xnorm2 != 0.f && fmaf(alpha, alpha, xnorm2) >= 1e-30f) {   // (below: counts as already reduced, see larfg)
                 const float ss = fmaf(alpha, alpha, xnorm2);
                 float rn = rsqrtf(ss);
                 rn = fmaf(0.5f * rn, fmaf(-ss * rn, rn, 1.0f), rn);

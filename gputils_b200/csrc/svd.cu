@@ -190,8 +190,10 @@ constexpr int JP = GPUB_JACOBI_PAIRS;   // pairs a warp rotates at once (4 or 2)
 constexpr int JRP = JP == 4 ? 16 : 8;   // values in the transpose-reduce (3 per pair, padded to a power of two)
 
 template<typename T> struct JacobiEps;
-template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; static constexpr double huge = 1.7e308; };
-template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; static constexpr float big = 1e15f; static constexpr float huge = 3.4e38f; };
+// floor: a pair whose product of squared norms (of the matrix scaled to order one) is below it is not rotated: the product -- and with it
+// the relative test c^2 > tol^2 a b -- underflows there, and columns that small only span the null space (replaced by the orthonormal completion)
+template<> struct JacobiEps<double> { static constexpr double v = 1.1102230246251565e-16; static constexpr double big = 1e100; static constexpr double huge = 1.7e308; static constexpr double floor = 1e-280; };
+template<> struct JacobiEps<float> { static constexpr float v = 5.9604645e-08f; static constexpr float big = 1e15f; static constexpr float huge = 3.4e38f; static constexpr float floor = 1e-30f; };
 
 // reciprocal square root / reciprocal from the MUFU seed plus Newton steps (~1 ulp, no slow-path call)
 template<typename T> __device__ __forceinline__ T jac_rsqrt(T x);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_rt(int n, const T *__restrict__ A
                             cc = __shfl_sync(0xffffffffu, tot, src + 2 * HS);
                     T cs = T(1), sn = T(0);
                     bool rot = false;
-                    if (((vmask >> (lane % JP)) & 1u) && cc != T(0) && cc * cc > tol2 * (aa * bb)) {
+                    if (((vmask >> (lane % JP)) & 1u) && cc != T(0) && cc * cc > tol2 * (aa * bb) && aa * bb > (T) JacobiEps<T>::floor) {
                         const T zeta = (bb - aa) * jac_rcp<T>(T(2) * cc);
                         const T az = fabs(zeta);
                         T t;
@@ -546,7 +548,7 @@ template<typename T>
 __device__ __forceinline__ bool jblk_params(T aa, T bb, T cc, T tol2, T &cs, T &sn, T &dl, T &tt, T &c2, T &ab) {
     cs = T(1); sn = T(0); dl = T(0); tt = T(0);
     c2 = cc * cc; ab = aa * bb;
-    if (cc == T(0) || c2 <= tol2 * ab) return false;
+    if (cc == T(0) || c2 <= tol2 * ab || !(ab > (T) JacobiEps<T>::floor)) return false;
     const T d = bb - aa, g = cc + cc;
     T t;
     if constexpr (sizeof(T) == 8 && GPUB_JBLK_T32) {
@@ -559,18 +561,20 @@ __device__ __forceinline__ bool jblk_params(T aa, T bb, T cc, T tol2, T &cs, T &
             double inv;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(m));
             const float df = (float) (d * inv), gf = (float) (g * inv);
-            const float h = fmaf(df, df, gf * gf);
-            float rh, rd;                                   // h is in [1/2, 1], den in [1/2, 2]: flush-to-zero forms, no range fix-ups
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(h));
-            const float den = fmaf(h, rh, fabsf(df));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(den));
-            float tf = gf * rd;
-            tf = d >= 0.0 ? tf : -tf;
-            tt = (double) tf * (double) tf;
-            cs = jac_rsqrt<T>(tt + T(1));
-            sn = cs * (double) tf;
-            dl = (double) tf * cc;
-            return true;
+            if (fabsf(gf) > 1e-30f) {                       // (below that the tangent leaves the single-precision range: FP64 path)
+                const float h = fmaf(df, df, gf * gf);
+                float rh, rd;                                   // h is in [1/2, 1], den in [1/2, 2]: flush-to-zero forms, no range fix-ups
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(h));
+                const float den = fmaf(h, rh, fabsf(df));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(den));
+                float tf = gf * rd;
+                tf = d >= 0.0 ? tf : -tf;
+                tt = (double) tf * (double) tf;
+                cs = jac_rsqrt<T>(tt + T(1));
+                sn = cs * (double) tf;
+                dl = (double) tf * cc;
+                return true;
+            }
         }
     }
     const T h2 = fma(d, d, g * g);
@@ -666,7 +670,7 @@ __device__ __forceinline__ void jblk_round(T (&c)[8][JE], T (&nn)[8], int lane, 
     T cs = T(1), sn = T(0), dl = T(0), tt = T(0);
     bool rot = false;
     const T c2 = cc * cc, ab = aa * bb;
-    if (cc != T(0) && !(c2 <= tol2 * ab)) {
+    if (cc != T(0) && !(c2 <= tol2 * ab) && ab > (T) JacobiEps<T>::floor) {
         const T zeta = (bb - aa) * jac_rcp<T>(T(2) * cc);
         const T az = fabs(zeta);
         T t;
