@@ -80,9 +80,31 @@ GPUB_HD inline T larfg(int n, T *alpha, T *x, long incx) {
     T xnorm = scale * t_sqrt(ssq);
     if (xnorm == T(0)) return T(0);
     T beta = -t_sign(lapy2(*alpha, xnorm), *alpha);
-    T tau = (beta - *alpha) / beta;
-    T s = T(1) / (*alpha - beta);
+    // dlarfg's guard: while |beta| is below safmin / eps, x, alpha and beta are scaled up by its reciprocal (the reciprocal of
+    // alpha - beta would overflow otherwise: an all-ones matrix in fp32 gets there in a dozen columns, each being rounding noise
+    // of the one before)
+    const T safmin = sizeof(T) == 8 ? T(2.0041683600089728e-292) : T(1.9721522630525295e-31);
+    const T rsafmn = T(1) / safmin;
+    int knt = 0;
+    T a = *alpha;
+    while (t_abs(beta) < safmin && knt < 20) {
+        knt++;
+        for (int i = 0; i < n - 1; i++) x[i * incx] *= rsafmn;
+        beta *= rsafmn;
+        a *= rsafmn;
+    }
+    if (knt > 0) {
+        // recompute the norm of the scaled vector (plain: it is in range now)
+        T ss = T(0);
+        for (int i = 0; i < n - 1; i++) ss += x[i * incx] * x[i * incx];
+        xnorm = t_sqrt(ss);
+        if (xnorm == T(0)) { *alpha = a; for (int j = 0; j < knt; j++) *alpha *= safmin; return T(0); }
+        beta = -t_sign(lapy2(a, xnorm), a);
+    }
+    T tau = (beta - a) / beta;
+    T s = T(1) / (a - beta);
     for (int i = 0; i < n - 1; i++) x[i * incx] *= s;
+    for (int j = 0; j < knt; j++) beta *= safmin;
     *alpha = beta;
     return tau;
 }
