@@ -290,11 +290,12 @@ __device__ __forceinline__ void jacobi_finish(int n, int ldx, T *X, T *s_sig, T 
     }
     __syncthreads();
     // rank sort, descending (ties broken by column index)
+    // (a NaN norm -- NaN in the input -- sorts first, like +inf: the ranks must stay a permutation, s_perm indexes shared memory)
     for (int p = tid; p < n; p += JT) {
-        const T sp = s_sig[p];
+        const T sp = s_sig[p] == s_sig[p] ? s_sig[p] : (T) JacobiEps<T>::huge;
         int rank = 0;
         for (int q = 0; q < n; q++) {
-            const T sq = s_sig[q];
+            const T sq = s_sig[q] == s_sig[q] ? s_sig[q] : (T) JacobiEps<T>::huge;
             rank += (sq > sp || (sq == sp && q < p)) ? 1 : 0;
         }
         s_perm[rank] = p;

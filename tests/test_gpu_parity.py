@@ -292,6 +292,25 @@ def test_gesvd_and_qr_of_degenerate_matrices(gpu_ctx, dt, m, n):
     assert np.isfinite(Q).all() and np.abs(Q.T @ Q - np.eye(m)).max() <= tol and np.abs(Q[:, :n] @ R - A[0]).max() <= tol * m
 
 
+@pytest.mark.parametrize("m,n", [(64, 16), (200, 24), (128, 64), (256, 128), (100, 40)])
+def test_gesvd_nan_input_does_not_fault(gpu_ctx, m, n):
+    """A NaN in the input poisons that matrix's result (as with LAPACK) but nothing else: no out-of-range index inside the kernels (the
+    Jacobi tail ranks column norms into a permutation that indexes shared memory), the other matrices of the batch are untouched, and
+    the context stays usable."""
+    import torch
+    from gputils_b200 import capi
+    rng = np.random.default_rng(m + 3 * n)
+    A = rng.uniform(-1, 1, (3, m, n))
+    A[1, m // 2, n // 3] = np.nan
+    S, U, Vt, info = capi.gesvd_batched(gpu_ctx, dev(A.copy()), True)
+    torch.cuda.synchronize()
+    Sn = S.cpu().numpy()
+    for i in (0, 2):
+        assert np.abs(Sn[i] - np.linalg.svd(A[i], compute_uv=False)).max() <= 1e-12 * 10
+    S2, _, _, info2 = capi.gesvd_batched(gpu_ctx, dev(A[:1].copy()), False)
+    assert torch.equal(S2[0], S[0])
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("m,n,want_u", [(64, 64, True), (128, 64, False), (192, 96, True)])
 def test_gesvd_chunked_batch_equals_small_batches(gpu_ctx, dt, m, n, want_u):
