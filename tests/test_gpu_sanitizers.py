@@ -62,3 +62,13 @@ def test_racecheck_on_every_kernel_family():
     out = _run(["--tool", "racecheck", "--kernel-name-exclude", "kernel_substring=k_potrf_pipe", sys.executable, "scripts/dev_sanitize.py"],
                timeout=2400)
     assert "done" in out and _errors(out) == 0, out[-4000:]
+
+
+def test_memcheck_and_racecheck_on_the_chunked_svd_and_the_nullspace_build():
+    """The library's own side streams: a batched SVD cut into sub-batches (fork / join by events, sliced workspace) and the Nullspace
+    build with the packing beside the projector."""
+    out = _run(["--tool", "memcheck", sys.executable, "scripts/dev_sanitize_chunked.py"], timeout=900)
+    assert "done" in out and _errors(out) == 0, out[-4000:]
+    out = _run(["--tool", "racecheck", sys.executable, "scripts/dev_sanitize_chunked.py"], timeout=900)
+    assert "done" in out and _errors(out) == 0, out[-4000:]
+
