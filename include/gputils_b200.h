@@ -241,6 +241,12 @@ int gpub_gels_batched_f32(gpub_ctx_t ctx, int sidx, size_t m, size_t n, float *A
  * A_i (m x n, m >= n) = U_i diag(S_i) Vt_i.  S descending, Vt is n x n, U is
  * the FULL m x m factor when jobu == 'A' and not referenced when jobu == 'N'.
  * A is destroyed.  info[i] = 0, or >0 if the iteration did not converge.
+ * A matrix whose largest entry is outside LAPACK's gesvd range [sqrt(safmin)/eps, eps/sqrt(safmin)] is scaled by a
+ * power of two first and its singular values scaled back (dlascl).  A batch of more matrices than the GPU has SMs
+ * runs as four sub-batches on streams of the library's own, forked from stream `sidx` and joined to it again before
+ * the call returns: work queued on stream `sidx` behind the call sees every result.
+ * Shapes: n <= 32 any m; 32 < n <= 256 while the n x n factor fits shared memory (fp64: n <= 167), else GPUB_ENOTSUP
+ * (worksize returns 0).
  * ref: tensor.cuh:1637, 1664 (gesvd, called numMats times in a host loop)     */
 size_t gpub_gesvd_batched_worksize_f64(size_t m, size_t n, int jobu, size_t batch);
 size_t gpub_gesvd_batched_worksize_f32(size_t m, size_t n, int jobu, size_t batch);
